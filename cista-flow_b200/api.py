@@ -1,0 +1,18 @@
+"""Public surface of the package (re-exported by ``cistaflow_b200``)."""
+from ._lib import CistaFlowError, LIB_PATH, load as load_library
+from .corr import CorrBlock, build_pyramid, coords_grid, lookup as corr_lookup
+from .event_process import (event_preprocess, event_preprocess_batched, event_preprocess_pytorch,
+                            events_to_voxel_grid, events_to_voxel_grid_batched, events_to_voxel_grid_pol,
+                            events_to_voxel_grid_pytorch)
+from .flow_utils import FrameWarp, backWarp, forwardWarp, warp, warp_frame_and_codes
+from .install import install, uninstall
+
+__all__ = [
+    "CistaFlowError", "LIB_PATH", "load_library",
+    "CorrBlock", "build_pyramid", "coords_grid", "corr_lookup",
+    "event_preprocess", "event_preprocess_batched", "event_preprocess_pytorch",
+    "events_to_voxel_grid", "events_to_voxel_grid_batched", "events_to_voxel_grid_pol",
+    "events_to_voxel_grid_pytorch",
+    "FrameWarp", "backWarp", "forwardWarp", "warp", "warp_frame_and_codes",
+    "install", "uninstall",
+]

@@ -1,0 +1,486 @@
+// Tensor-core all-pairs correlation for sm_100a:
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring ->
+//   tcgen05.mma kind::tf32 (accumulators in TMEM) -> tcgen05.ld epilogue with
+//   fused 1/sqrt(D) scale and fused level-1 (2x2) average pooling.
+//
+// Replaces the torch.matmul + first avg_pool2d of CorrBlock.__init__
+// (ERAFT/corr.py:19-27,52-60; DCEIFlow/core/corr/raft_corr.py:22-30,56-65).
+//
+// GEMM view, per batch item b:   C[i, j] = sum_k A[k, i] * Bm[k, j]
+//   A = fmap1[b] (D x N), Bm = fmap2[b] (D x N), N = h*w contiguous: BOTH
+//   operands are "MN-major" (the reference's fmap1.transpose(1,2) is free).
+//   The tiles are loaded as TMA boxes of 32 (MN, 128 bytes) x 32 (K rows) which
+//   land in the canonical UMMA MN-major SWIZZLE_128B layout:
+//   ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units, LBO = 4096 B between
+//   32-column atoms (one TMA box each), SBO = 1024 B between groups of 8 K rows.
+//   One tcgen05.mma kind::tf32 has K = 8, i.e. consumes one 8-row group: the
+//   descriptor start address advances by 1024 B per MMA.
+//
+// Tile: 128 queries (M, TMEM lanes) x BN targets (TMEM columns).  With pooling
+// fused, BN = R*w covers R (even) whole rows of the target map so that each 2x2
+// pooling window lives inside one accumulator row; the epilogue thread that owns
+// query i reads row y and row y+1 of its TMEM lane, stores both level-0 rows and
+// the pooled level-1 row.  Level 0 (N^2 floats) is therefore written once and
+// never re-read: the volume is HBM-write bound (96 FLOP/B).
+//
+// Persistent, warp-specialised CTA (1 per SM, 192 threads):
+//   warps 0-3  epilogue (TMEM lane quarter = warp id), TMEM -> registers -> global
+//   warp  4    TMA producer (one elected lane)
+//   warp  5    TMEM allocator + MMA issuer (one elected lane)
+// Two TMEM accumulator stages (2 x 256 columns) let the MMA of tile t+1 overlap
+// the epilogue of tile t; a 4-stage shared-memory ring feeds the MMA.
+//
+// Operand precision: tcgen05 kind::tf32 reads fp32 words and ignores the low 13
+// mantissa bits (truncation), which biases every product low by ~1e-3 relative.
+// A pre-pass rounds the feature maps to TF32 with round-to-nearest
+// (cvt.rna.tf32.f32) into the workspace, making the error unbiased
+// (max |err| ~ 3e-4 * max|ref| at D=256, within the 1e-3 gate).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace cf {
+
+namespace tc {
+
+constexpr int BM = 128;          // queries per tile (UMMA M)
+constexpr int BK = 32;           // K rows per pipeline stage (4 MMAs of K=8)
+constexpr int STAGES = 4;
+constexpr int MAX_BN = 256;      // UMMA N limit
+constexpr int BOX_BYTES = 32 * 32 * 4;                 // one TMA box: 32 cols x 32 rows fp32
+constexpr int A_BYTES = (BM / 32) * BOX_BYTES;         // 16 KB
+constexpr int B_BYTES = (MAX_BN / 32) * BOX_BYTES;     // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;         // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;  // ~seconds; a stuck pipeline traps instead of hanging the GPU
+
+struct Params {
+    int B, D, N, h, w;
+    int BN;        // valid target columns per tile
+    int BN_mma;    // UMMA N (BN rounded up to 16)
+    int n_boxes_b; // TMA boxes per stage for the B operand
+    int R;         // target rows per tile when pooling is fused (0 = not fused)
+    int tiles_m, tiles_n, total_tiles;
+    int h1, w1;    // level-1 map size
+    float scale;
+    int stream_l0; // 1: level 0 is larger than L2 can hold -> evict-first stores
+    float *l0;
+    float *l1;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 operands, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread t <- lane (base+t), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, MN-major, SWIZZLE_128B (see file header)
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address            bits [0,14)
+    d |= (uint64_t)(4096u >> 4) << 16;               // leading byte offset (MN) bits [16,30)
+    d |= (uint64_t)(1024u >> 4) << 32;               // stride byte offset (K)   bits [32,46)
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both MN-major, M=128, N=n
+__host__ __device__ inline uint32_t make_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void decode_tile(const Params &p, int tile, int &b, int &mb, int &nb) {
+    nb = tile % p.tiles_n;
+    const int t = tile / p.tiles_n;
+    mb = t % p.tiles_m;
+    b = t / p.tiles_m;
+}
+
+template <bool STREAM>
+__device__ __forceinline__ void store_row_chunk_impl(float *dst, const uint32_t (&v)[32], float scale, int nvalid, bool vec4) {
+    // nvalid in [0,32], multiple of 4 when vec4
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (vec4) {
+            if (4 * q < nvalid) {
+                const float4 o = make_float4(__uint_as_float(v[4 * q]) * scale, __uint_as_float(v[4 * q + 1]) * scale,
+                                             __uint_as_float(v[4 * q + 2]) * scale, __uint_as_float(v[4 * q + 3]) * scale);
+                if (STREAM) __stcs(reinterpret_cast<float4 *>(dst) + q, o);
+                else *(reinterpret_cast<float4 *>(dst) + q) = o;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (4 * q + r < nvalid) {
+                    const float o = __uint_as_float(v[4 * q + r]) * scale;
+                    if (STREAM) __stcs(dst + 4 * q + r, o);
+                    else dst[4 * q + r] = o;
+                }
+        }
+    }
+}
+__device__ __forceinline__ void store_row_chunk(float *dst, const uint32_t (&v)[32], float scale, int nvalid, bool vec4, bool stream) {
+    if (stream) store_row_chunk_impl<true>(dst, v, scale, nvalid, vec4);
+    else store_row_chunk_impl<false>(dst, v, scale, nvalid, vec4);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + STAGES;
+    uint64_t *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = p.D / BK;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = (uint32_t)(BM / 32 + p.n_boxes_b) * BOX_BYTES;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int b, mb, nb;
+                decode_tile(p, tile, b, mb, nb);
+                const int i0 = mb * BM, j0 = nb * p.BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + A_BYTES;
+                    mbar_expect_tx(&full[stage], tx_bytes);
+                    const int krow = b * p.D + kb * BK;
+#pragma unroll
+                    for (int a = 0; a < BM / 32; ++a) tma_load_2d(sa + a * BOX_BYTES, &tmap_a, i0 + 32 * a, krow, &full[stage]);
+                    for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOX_BYTES, &tmap_b, j0 + 32 * a, krow, &full[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // -------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            const uint32_t idesc = make_idesc_tf32(p.BN_mma);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < BK / 8; ++kk)
+                        umma_tf32(d_tmem, make_desc_mn_sw128(sa + kk * 1024), make_desc_mn_sw128(sb + kk * 1024), idesc,
+                                  (uint32_t)((kb | kk) != 0));
+                    umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int row = 32 * warp + lane;
+        const bool vec4_l0 = (p.N % 4) == 0 && (p.w % 4) == 0;
+        const bool vec4_l1 = (p.w1 % 4) == 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int b, mb, nb;
+            decode_tile(p, tile, b, mb, nb);
+            const int i = mb * BM + row;
+            const bool row_ok = i < p.N;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)acc * MAX_BN;
+            float *l0row = p.l0 + ((size_t)b * p.N + (row_ok ? i : 0)) * p.N;
+            if (p.R == 0) {
+                const int j0 = nb * p.BN;
+                for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    int nvalid = min(32, min(p.BN - c0, p.N - (j0 + c0)));
+                    if (row_ok && nvalid > 0) store_row_chunk(l0row + j0 + c0, v, p.scale, nvalid, vec4_l0 && (nvalid % 4 == 0), p.stream_l0 != 0);
+                }
+            } else {
+                const int y0 = nb * p.R;
+                float *l1map = p.l1 + ((size_t)b * p.N + (row_ok ? i : 0)) * p.h1 * p.w1;
+                for (int pr = 0; pr < p.R; pr += 2) {
+                    const int y = y0 + pr;
+                    if (y + 1 >= p.h) break;  // warp-uniform
+                    for (int xc = 0; xc < p.w; xc += 32) {
+                        uint32_t ra[32], rc[32];
+                        tmem_ld32(taddr + pr * p.w + xc, ra);
+                        tmem_ld32(taddr + (pr + 1) * p.w + xc, rc);
+                        tmem_ld_wait();
+                        const int nvalid = min(32, p.w - xc);
+                        if (row_ok) {
+                            store_row_chunk(l0row + (size_t)y * p.w + xc, ra, p.scale, nvalid, vec4_l0, p.stream_l0 != 0);
+                            store_row_chunk(l0row + (size_t)(y + 1) * p.w + xc, rc, p.scale, nvalid, vec4_l0, p.stream_l0 != 0);
+                            // ATen avg_pool2d: ((a + b) + c) + d, then / 4, on the stored (scaled) values
+                            float *dst = l1map + (size_t)(y >> 1) * p.w1 + (xc >> 1);
+                            const int npool = min(16, p.w1 - (xc >> 1));
+                            float o[16];
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                float s = __uint_as_float(ra[2 * q]) * p.scale + __uint_as_float(ra[2 * q + 1]) * p.scale;
+                                s += __uint_as_float(rc[2 * q]) * p.scale;
+                                s += __uint_as_float(rc[2 * q + 1]) * p.scale;
+                                o[q] = s * 0.25f;
+                            }
+                            if (vec4_l1) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    if (4 * q < npool)
+                                        *(reinterpret_cast<float4 *>(dst) + q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    if (2 * q < npool) *(reinterpret_cast<float2 *>(dst) + q) = make_float2(o[2 * q], o[2 * q + 1]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// fp32 -> tf32 round-to-nearest (ties away), 4 elements per thread
+__global__ void __launch_bounds__(256) tf32_round_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b,
+                                                         float4 *__restrict__ oa, float4 *__restrict__ ob, int64_t n4) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n4; i += stride) {
+        const bool second = i >= n4;
+        const int64_t k = second ? i - n4 : i;
+        float4 v = __ldg((second ? b : a) + k);
+        uint32_t x, y, z, w;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x) : "f"(v.x));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(v.y));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(z) : "f"(v.z));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(w) : "f"(v.w));
+        (second ? ob : oa)[k] = make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(w));
+    }
+}
+
+// ---- host side --------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D map over a feature map viewed as [B*D rows, N cols], box 32 x 32, 128B swizzle
+static int make_fmap_tmap(CUtensorMap *m, const float *base, int B, int D, int N, CUtensorMapDataType dt) {
+    EncodeTiledFn fn = encode_fn();
+    CF_REQUIRE(fn, CF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)B * D};
+    cuuint64_t strides[1] = {(cuuint64_t)N * sizeof(float)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, dt, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return CF_OK;
+}
+
+}  // namespace tc
+
+bool corr_tensor_core_supported(int D, int h, int w) {
+    return D % tc::BK == 0 && ((int64_t)h * w) % 4 == 0;
+}
+
+size_t corr_tc_workspace_bytes(int B, int D, int h, int w) {
+    return 2 * align_up((size_t)B * D * h * w * sizeof(float), 256);
+}
+
+// flags (debug/experiments, env CF_TC_FLAGS): bit0 = skip the RN pre-pass (feed raw fp32, hardware truncation),
+// bit1 = encode the tensor maps as TFLOAT32 instead of FLOAT32, bit2 = never fuse the pooling.
+int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int h, int w, float scale, float *level0,
+                            float *level1, int precision, void *ws, size_t ws_bytes, int flags, int *fused_level1,
+                            cudaStream_t stream) {
+    using namespace tc;
+    CF_REQUIRE(precision == CF_CORR_TF32, CF_ERR_UNSUPPORTED, "cf_corr_build: CF_CORR_3XTF32 is not implemented yet");
+    CF_REQUIRE(aligned16(f1) && aligned16(f2) && aligned16(level0), CF_ERR_ALIGN, "cf_corr_build: tensors must be 16-byte aligned");
+    const int N = h * w;
+    const float *a = f1, *bm = f2;
+    if (!(flags & 1)) {
+        const size_t half = align_up((size_t)B * D * N * sizeof(float), 256);
+        CF_REQUIRE(ws && ws_bytes >= 2 * half, CF_ERR_WORKSPACE, "cf_corr_build: workspace too small (%zu < %zu)", ws_bytes, 2 * half);
+        CF_REQUIRE(aligned16(ws), CF_ERR_ALIGN, "cf_corr_build: workspace not 16-byte aligned");
+        float *ra = reinterpret_cast<float *>(ws), *rb = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + half);
+        const int64_t n4 = (int64_t)B * D * N / 4;
+        const int64_t blocks = ceil_div(2 * n4, 256);
+        tf32_round_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(
+            reinterpret_cast<const float4 *>(f1), reinterpret_cast<const float4 *>(f2), reinterpret_cast<float4 *>(ra),
+            reinterpret_cast<float4 *>(rb), n4);
+        CF_LAUNCH_CHECK("tf32_round_kernel");
+        a = ra;
+        bm = rb;
+    }
+    Params p{};
+    p.B = B; p.D = D; p.N = N; p.h = h; p.w = w; p.scale = scale; p.l0 = level0; p.l1 = level1;
+    p.h1 = h / 2; p.w1 = w / 2;
+    // R = number of whole target rows per tile (even).  The epilogue reads 32-column chunks, so the
+    // last chunk of the last row must stay inside the 256-column accumulator stage.
+    int R = 0;
+    if (level1 != nullptr && !(flags & 4) && (w % 4 == 0) && (h % 2 == 0) && 2 * w <= MAX_BN) {
+        R = 2 * (MAX_BN / (2 * w));
+        if (R > h) R = h;
+        while (R > 0 && (R - 1) * w + (int)align_up(w, 32) > MAX_BN) R -= 2;
+    }
+    *fused_level1 = R > 0;
+    p.stream_l0 = (int64_t)B * N * N * 4 > (64ll << 20);
+    if (R > 0) {
+        p.R = R;
+        p.BN = R * w;
+        p.tiles_n = (int)ceil_div(h, R);
+    } else {
+        p.R = 0;
+        p.BN = N < MAX_BN ? (int)align_up(N, 16) : MAX_BN;
+        p.tiles_n = (int)ceil_div(N, p.BN);
+    }
+    p.BN_mma = (int)align_up(p.BN, 16);
+    p.n_boxes_b = (int)ceil_div(p.BN_mma, 32);
+    p.tiles_m = (int)ceil_div(N, BM);
+    const int64_t total = (int64_t)B * p.tiles_m * p.tiles_n;
+    CF_REQUIRE(total < (1ll << 31), CF_ERR_INVALID_ARG, "cf_corr_build: too many tiles");
+    p.total_tiles = (int)total;
+
+    const CUtensorMapDataType dt = (flags & 2) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUtensorMap ta, tb;
+    if (int rc = make_fmap_tmap(&ta, a, B, D, N, dt)) return rc;
+    if (int rc = make_fmap_tmap(&tb, bm, B, D, N, dt)) return rc;
+
+    int dev = 0;
+    CF_CUDA(cudaGetDevice(&dev));
+    static bool opt_in[64] = {};
+    if (!opt_in[dev & 63]) {
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        opt_in[dev & 63] = true;
+    }
+    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    corr_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+    CF_LAUNCH_CHECK("corr_tc_kernel");
+    return CF_OK;
+}
+
+}  // namespace cf

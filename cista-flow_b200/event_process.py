@@ -1,0 +1,187 @@
+"""Event stream -> voxel grid: B200 mirror of the reference's ``utils/event_process.py``.
+
+Same names, argument meaning and return types as the reference, so that
+``from utils.event_process import events_to_voxel_grid, event_preprocess`` can
+be re-pointed here (see ``install.py``):
+
+  events_to_voxel_grid(events, num_bins, width, height, is_reverse=False)
+        -> np.ndarray float32 [nb,H,W]            (utils/event_process.py:15-72)
+  events_to_voxel_grid_pol(events, num_bins, width, height)
+        -> np.ndarray float32 [nb,2,H,W]          (utils/event_process.py:75-123)
+  events_to_voxel_grid_pytorch(events, num_bins, width, height)
+        -> torch.Tensor float32 [nb,H,W] on events.device   (:127-190)
+  event_preprocess(grid, mode='std', filter_hot_pixel=False)          (:193-216)
+  event_preprocess_pytorch(grid, mode='std', filter_hot_pixel=False)  (:219-239)
+
+plus the batched device-resident form the GPU path is designed around
+(``events_to_voxel_grid_batched``): many windows per launch, fused statistics
+and normalisation, result stays in HBM for the network.
+
+All arithmetic runs in ``libcistaflow.so`` on the GPU (NumPy/CPU inputs are
+staged to the current CUDA device and the result copied back, so the drop-in
+contract "result lives where the input lived" is kept).  Differences from the
+reference, all deliberate:
+  * inputs are never mutated (the reference rewrites ``events[:,3]`` and
+    ``events[:,0]`` in place, :51/:159);
+  * ``event_preprocess`` returns float32 (the reference silently returns
+    float64 under NumPy >= 2);
+  * events with (x, y) outside the grid are dropped instead of raising.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# 'atomic' (fast, <=1e-5 rel.) or 'deterministic' (bit-exact vs the reference's
+# sequential accumulation).  Override per call with mode=... or globally here.
+DEFAULT_MODE = os.environ.get("CISTAFLOW_VOXEL_MODE", "atomic")
+
+_MODES = {"atomic": _lib.VOXEL_ATOMIC, "deterministic": _lib.VOXEL_DETERMINISTIC}
+_PRE = {None: _lib.PRE_NONE, "none": _lib.PRE_NONE, "std": _lib.PRE_STD, "maxmin": _lib.PRE_MAXMIN}
+_FLAVOURS = {"torch": _lib.FLAVOUR_TORCH, "numpy": _lib.FLAVOUR_NUMPY, "pol": _lib.FLAVOUR_POL}
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("cistaflow_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _check_args(events, num_bins, width, height):
+    # same asserts as the reference (utils/event_process.py:23-26)
+    assert events.shape[1] == 4
+    assert num_bins > 0
+    assert width > 0
+    assert height > 0
+
+
+def events_to_voxel_grid_batched(events: torch.Tensor, offsets: torch.Tensor, num_bins: int, width: int,
+                                 height: int, normalize: str | None = None, filter_hot_pixel: bool = False,
+                                 hot_threshold: float | None = None, flavour: str = "numpy",
+                                 mode: str | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """B windows in one launch.
+
+    events   float64 CUDA tensor [sum N_b, 4] rows (t, x, y, p), windows concatenated
+    offsets  int64 CUDA tensor [B+1]
+    returns  float32 [B, nb, H, W] ([B, nb, 2, H, W] for flavour='pol') on the same device
+
+    ``normalize`` fuses ``event_preprocess`` ('std' / 'maxmin'); the hot-pixel
+    threshold defaults to the reference's 25/nb (flavour numpy/pol) or 20/nb
+    (flavour torch) when ``filter_hot_pixel`` is set.
+    """
+    _lib.require_cuda(events, "events")
+    _lib.require_cuda(offsets, "offsets")
+    _check_args(events, num_bins, width, height)
+    if events.dtype != torch.float64:
+        events = events.double()
+    events = events.contiguous()
+    offsets = offsets.to(torch.int64).contiguous()
+    B = offsets.numel() - 1
+    mode_id = _MODES[mode or DEFAULT_MODE]
+    flav = _FLAVOURS[flavour]
+    pre = _PRE[normalize]
+    thr = 0.0
+    if filter_hot_pixel:
+        thr = hot_threshold if hot_threshold is not None else (20.0 if flavour == "torch" else 25.0) / num_bins
+    shape = (B, num_bins, 2, height, width) if flavour == "pol" else (B, num_bins, height, width)
+    dev = events.device
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+    else:
+        assert out.shape == shape and out.dtype == torch.float32 and out.is_contiguous() and out.device == dev
+    lib = _lib.load()
+    total = events.shape[0]
+    with torch.cuda.device(dev):
+        ws_bytes = lib.cf_voxel_workspace_bytes(total, B, num_bins, height, width, mode_id, flav, pre)
+        ws = _lib.workspace(ws_bytes, dev)
+        rc = lib.cf_voxel_bin(_lib.ptr(events) if total else None, offsets.data_ptr(), total, B, num_bins, height,
+                              width, mode_id, flav, pre, thr, out.data_ptr(), _lib.ptr(ws), ws_bytes,
+                              _lib.stream_ptr(dev))
+    _lib.check(rc, "cf_voxel_bin")
+    return out
+
+
+def _single_window(events_dev: torch.Tensor, num_bins, width, height, flavour, mode, **kw) -> torch.Tensor:
+    n = events_dev.shape[0]
+    offsets = torch.tensor([0, n], dtype=torch.int64, device=events_dev.device)
+    return events_to_voxel_grid_batched(events_dev, offsets, num_bins, width, height, flavour=flavour, mode=mode, **kw)[0]
+
+
+def events_to_voxel_grid(events, num_bins, width, height, is_reverse=False, mode=None):
+    """Drop-in for ``utils/event_process.py:15-72`` (NumPy in, NumPy float32 out)."""
+    _check_args(events, num_bins, width, height)
+    ev = np.ascontiguousarray(events, dtype=np.float64)
+    if is_reverse:
+        # :33-34 flips the stream; :51-54 then maps EVERY polarity to -1 (sic)
+        ev = ev[::-1].copy()
+        ev[:, 3] = -1.0
+    dev = _device()
+    ev_dev = torch.from_numpy(ev).to(dev)
+    return _single_window(ev_dev, num_bins, width, height, "numpy", mode).cpu().numpy()
+
+
+def events_to_voxel_grid_pol(events, num_bins, width, height, mode=None):
+    """Drop-in for ``utils/event_process.py:75-123`` -> float32 [nb,2,H,W]."""
+    _check_args(events, num_bins, width, height)
+    ev_dev = torch.from_numpy(np.ascontiguousarray(events, dtype=np.float64)).to(_device())
+    return _single_window(ev_dev, num_bins, width, height, "pol", mode).cpu().numpy()
+
+
+def events_to_voxel_grid_pytorch(events, num_bins, width, height, mode=None):
+    """Drop-in for ``utils/event_process.py:127-190``: result on ``events.device``."""
+    _check_args(events, num_bins, width, height)
+    with torch.no_grad():
+        src = events.device
+        ev_dev = events if events.is_cuda else events.to(_device())
+        grid = _single_window(ev_dev, num_bins, width, height, "torch", mode)
+        return grid if src == grid.device else grid.to(src)
+
+
+def event_preprocess_batched(grids: torch.Tensor, mode: str = "std", filter_hot_pixel: bool = False,
+                             hot_threshold: float | None = None, variant: str = "numpy",
+                             out: torch.Tensor | None = None) -> torch.Tensor:
+    """``event_preprocess`` on a CUDA batch [B, nb, H, W]; statistics per window."""
+    _lib.require_cuda(grids, "grids")
+    assert mode in ("std", "maxmin"), "mode must be 'maxmin' or 'std'"
+    g = grids.float().contiguous()
+    B = g.shape[0]
+    cells = g[0].numel()
+    nb = g.shape[1]
+    thr = 0.0
+    if filter_hot_pixel:
+        thr = hot_threshold if hot_threshold is not None else (20.0 if variant == "torch" else 25.0) / nb
+    if out is None:
+        out = torch.empty_like(g)
+    lib = _lib.load()
+    with torch.cuda.device(g.device):
+        ws_bytes = lib.cf_preprocess_workspace_bytes(B, cells)
+        ws = _lib.workspace(ws_bytes, g.device)
+        rc = lib.cf_voxel_preprocess(g.data_ptr(), out.data_ptr(), B, cells, _PRE[mode], thr, _lib.ptr(ws), ws_bytes,
+                                     _lib.stream_ptr(g.device))
+    _lib.check(rc, "cf_voxel_preprocess")
+    return out
+
+
+def event_preprocess(event_voxel_grid, mode="std", filter_hot_pixel=False):
+    """Drop-in for ``utils/event_process.py:193-216`` (NumPy in/out, 25/nb threshold)."""
+    assert mode == "maxmin" or mode == "std"
+    g = torch.from_numpy(np.ascontiguousarray(event_voxel_grid, dtype=np.float32)).to(_device())
+    return event_preprocess_batched(g[None], mode, filter_hot_pixel, variant="numpy")[0].cpu().numpy()
+
+
+def event_preprocess_pytorch(event_voxel_grid, mode="std", filter_hot_pixel=False):
+    """Drop-in for ``utils/event_process.py:219-239`` (torch in/out, 20/nb threshold).
+    Like the reference, an unknown ``mode`` returns the (hot-pixel filtered) input."""
+    src = event_voxel_grid.device
+    g = event_voxel_grid if event_voxel_grid.is_cuda else event_voxel_grid.to(_device())
+    if mode not in ("std", "maxmin"):
+        g = g.clone()
+        if filter_hot_pixel:
+            g[abs(g) > 20.0 / g.shape[0]] = 0
+        return g.to(src)
+    res = event_preprocess_batched(g[None], mode, filter_hot_pixel, variant="torch")[0]
+    return res if src == res.device else res.to(src)

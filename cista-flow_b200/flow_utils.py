@@ -1,0 +1,114 @@
+"""Flow-guided warp: B200 mirror of the reference's ``utils/flow_utils.py``.
+
+Same classes and signatures (``backWarp(W, H)``, ``forwardWarp(W, H)``,
+``FrameWarp(mode).warp_frame(I, flow)``, utils/flow_utils.py:40-221).  In the
+reference both "modes" are a bilinear gather through ``grid_sample`` and differ
+only in the sign of the flow; one CUDA kernel (``cf_warp``)
+serves both.  ``warp_frame_and_codes`` is the fused per-frame step of
+``e2v/e2v_model.py:188-191`` (image + sparse codes, x0.5 flow down-sampling
+done inside the kernel).
+
+Inference only: the kernels have no backward (the reference's evaluation
+drivers run under ``torch.no_grad()``); a tensor that requires grad raises.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
+    _lib.require_cuda(t, name)
+    if torch.is_grad_enabled() and t.requires_grad:
+        raise RuntimeError(f"cistaflow_b200 warp is inference-only: {name} requires grad "
+                           f"(run under torch.no_grad(); the backward/splat kernel is not built yet)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def warp(img: torch.Tensor, flow: torch.Tensor, sign: float, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out[b,c,y,x] = bilinear(img[b,c], reflect((x+sign*u)(W-1)/W, (y+sign*v)(H-1)/H)).
+
+    ``flow`` is either at the image's resolution or at twice the resolution
+    (then the reference's x0.5 bilinear align_corners=True down-sampling is
+    fused, values not rescaled)."""
+    img, flow = _prep(img, "img"), _prep(flow, "flow")
+    assert img.dim() == 4 and flow.dim() == 4 and flow.shape[1] == 2 and flow.shape[0] == img.shape[0]
+    assert img.device == flow.device
+    B, C, H, W = img.shape
+    if out is None:
+        out = torch.empty_like(img)
+    lib = _lib.load()
+    with torch.cuda.device(img.device):
+        rc = lib.cf_warp(img.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, flow.shape[2], flow.shape[3],
+                         float(sign), _lib.stream_ptr(img.device))
+    _lib.check(rc, "cf_warp")
+    return out
+
+
+def warp_frame_and_codes(img: torch.Tensor, codes: torch.Tensor, flow: torch.Tensor, mode: str = "forward"):
+    """One launch for ``e2v/e2v_model.py:188-191``: returns (warped image, warped codes).
+    img [B,Ci,H,W], codes [B,Cz,H//2,W//2], flow [B,2,H,W]."""
+    img, codes, flow = _prep(img, "img"), _prep(codes, "codes"), _prep(flow, "flow")
+    B, Ci, H, W = img.shape
+    assert flow.shape == (B, 2, H, W), "flow must be [B,2,H,W] at the image resolution"
+    assert codes.shape[0] == B and codes.shape[2] == H // 2 and codes.shape[3] == W // 2, \
+        "codes must be [B,C,H//2,W//2]"
+    img_out, codes_out = torch.empty_like(img), torch.empty_like(codes)
+    sign = -1.0 if mode == "forward" else 1.0
+    lib = _lib.load()
+    with torch.cuda.device(img.device):
+        rc = lib.cf_warp_frame_and_codes(img.data_ptr(), codes.data_ptr(), flow.data_ptr(), img_out.data_ptr(),
+                                         codes_out.data_ptr(), B, Ci, codes.shape[1], H, W, sign,
+                                         _lib.stream_ptr(img.device))
+    _lib.check(rc, "cf_warp_frame_and_codes")
+    return img_out, codes_out
+
+
+class backWarp(nn.Module):
+    """I0 = backwarp(I1, F_0_1): gather at (x+u, y+v)  (utils/flow_utils.py:40-120).
+    Note the (W, H) argument order of the reference."""
+
+    def __init__(self, W, H):
+        super().__init__()
+        self.W, self.H = W, H
+
+    def forward(self, img, flow):
+        return warp(img, flow, +1.0)
+
+
+class forwardWarp(nn.Module):
+    """I1 = forwardwarp(I0, F_0_1): gather at (x-u, y-v)  (utils/flow_utils.py:123-190)."""
+
+    def __init__(self, W, H):
+        super().__init__()
+        self.W, self.H = W, H
+
+    def forward(self, img, flow):
+        return warp(img, flow, -1.0)
+
+
+class FrameWarp(object):
+    """utils/flow_utils.py:193-221: dispatch on mode, one cached module per (W, H)."""
+
+    def __init__(self, mode):
+        self.mode = mode
+        self.flowWarp_dict = dict()
+
+    def get_flowWarp_module(self, width: int, height: int):
+        module = self.flowWarp_dict.get((width, height))
+        if module is None:
+            module = forwardWarp(width, height) if self.mode == "forward" else backWarp(width, height)
+            self.flowWarp_dict[(width, height)] = module
+        return module
+
+    def warp_frame(self, I, flow):
+        height, width = I.shape[-2:]
+        return self.get_flowWarp_module(width, height)(I, flow)
+
+    def warp_frame_and_codes(self, I, Z, flow):
+        """Fused image + codes step (extension; not in the reference)."""
+        return warp_frame_and_codes(I, Z, flow, self.mode)

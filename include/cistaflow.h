@@ -1,0 +1,174 @@
+/*
+ * cistaflow.h -- C ABI of libcistaflow.so: the CISTA-Flow per-frame
+ * motion-compensation hot path as hand-written sm_100a (B200) CUDA.
+ *
+ * The reference (lsying009/CISTA-Flow) is pure Python: it has no FFI of its own
+ * (SURVEY.md F1), its boundary is a set of Python functions/classes.  Each entry
+ * point below names the reference interface it replaces (file:line, relative to
+ * the reference checkout).  The Python mirror of those interfaces lives in
+ * cista-flow_b200/ and binds this header through ctypes (INTEGRATION.md shows the
+ * stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter is documented as
+ *     "host array"; the library never allocates or frees device memory and never
+ *     synchronises the host: all work is enqueued on `stream` (graph-capturable);
+ *   - tensors are dense, row-major ("NCHW"), float32 unless stated;
+ *   - float32/float64 tensors must be 16-byte aligned (torch allocations are);
+ *   - return value: CF_OK (0) or a negative cf_status; cf_last_error() returns a
+ *     thread-local human-readable message for the last failure;
+ *   - there is no CPU fallback: on a device that is not compute capability 10.x
+ *     every compute entry point returns CF_ERR_ARCH.
+ */
+#ifndef CISTAFLOW_H_
+#define CISTAFLOW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CISTAFLOW_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#if defined(__GNUC__)
+#define CF_API __attribute__((visibility("default")))
+#else
+#define CF_API
+#endif
+
+typedef void *cf_stream_t; /* a cudaStream_t */
+
+typedef enum cf_status {
+    CF_OK = 0,
+    CF_ERR_INVALID_ARG = -1, /* bad shape / size / enum value              */
+    CF_ERR_NULL = -2,        /* required pointer is NULL                    */
+    CF_ERR_ALIGN = -3,       /* pointer not 16-byte aligned                 */
+    CF_ERR_ARCH = -4,        /* current device is not sm_100 (B200)         */
+    CF_ERR_WORKSPACE = -5,   /* workspace missing or too small              */
+    CF_ERR_CUDA = -6,        /* a CUDA runtime/driver call failed           */
+    CF_ERR_UNSUPPORTED = -7  /* valid request this build does not implement */
+} cf_status;
+
+CF_API int cf_version(void);
+CF_API const char *cf_last_error(void);
+/* CF_OK when the CURRENT device can run the kernels (compute capability 10.x). */
+CF_API int cf_device_check(void);
+
+/* ------------------------------------------------------------------------- *
+ * Part 1: event stream -> voxel grid (+ normalisation)
+ * replaces  utils/event_process.py:15-72    events_to_voxel_grid        (flavour NUMPY)
+ *           utils/event_process.py:127-190  events_to_voxel_grid_pytorch (flavour TORCH)
+ *           utils/event_process.py:75-123   events_to_voxel_grid_pol     (flavour POL)
+ *           utils/event_process.py:193-239  event_preprocess(_pytorch)   (preprocess != NONE)
+ * ------------------------------------------------------------------------- */
+typedef enum cf_voxel_mode {
+    CF_VOXEL_ATOMIC = 0,       /* fast: fp32 atomics, sum order unspecified (<= 1e-5 rel.)   */
+    CF_VOXEL_DETERMINISTIC = 1 /* bit-exact: per-cell sums in the reference's event order    */
+} cf_voxel_mode;
+
+typedef enum cf_voxel_flavour {
+    CF_FLAVOUR_TORCH = 0, /* fp32 weights, fp32 adds                  (event_process.py:166-187) */
+    CF_FLAVOUR_NUMPY = 1, /* fp64 weights, fp64 add rounded to fp32    (event_process.py:56-66)   */
+    CF_FLAVOUR_POL = 2    /* [nb,2,H,W], channel = polarity, |weights| (event_process.py:104-119) */
+} cf_voxel_flavour;
+
+typedef enum cf_preprocess {
+    CF_PRE_NONE = 0,
+    CF_PRE_STD = 1,   /* mask*(v-mean)/(std+1e-8) over the NON-ZERO entries of each window */
+    CF_PRE_MAXMIN = 2 /* (v-min)/(max-min+1e-8)                                            */
+} cf_preprocess;
+
+/*
+ * events   float64 [total_events, 4] rows (t, x, y, p); the windows are
+ *          concatenated, each sorted by t; p == 0 means negative polarity.
+ *          fp64 is part of the contract: absolute stamps do not fit fp32
+ *          (data_readers/event_readers.py:15-20).
+ * offsets  int64 [B+1] (DEVICE), window b = rows [offsets[b], offsets[b+1]).
+ * out      float32 [B, nb, H, W]   (flavour POL: [B, nb, 2, H, W]).
+ * hot_thr  > 0: entries with |v| > hot_thr are zeroed before the statistics
+ *          (25/nb in event_preprocess, 20/nb in event_preprocess_pytorch);
+ *          <= 0 disables.  Ignored when preprocess == CF_PRE_NONE.
+ * Events whose (x, y) fall outside the grid are dropped (the reference would
+ * raise IndexError; its callers pre-filter, data_readers/video_readers.py:208).
+ * An empty window yields an all-zero grid (event_process.py:36-37).
+ */
+CF_API size_t cf_voxel_workspace_bytes(int64_t total_events, int B, int nb, int H, int W,
+                                int mode, int flavour, int preprocess);
+CF_API int cf_voxel_bin(const double *events, const int64_t *offsets, int64_t total_events,
+                 int B, int nb, int H, int W, int mode, int flavour,
+                 int preprocess, float hot_thr, float *out,
+                 void *workspace, size_t workspace_bytes, cf_stream_t stream);
+
+/* event_preprocess(_pytorch) on an existing batch of grids [B, C, H, W]
+ * (utils/event_process.py:193-239).  in == out is allowed. */
+CF_API size_t cf_preprocess_workspace_bytes(int B, int64_t cells_per_window);
+CF_API int cf_voxel_preprocess(const float *in, float *out, int B, int64_t cells_per_window,
+                        int preprocess, float hot_thr,
+                        void *workspace, size_t workspace_bytes, cf_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Part 2: flow-guided bilinear warp (a gather in BOTH warp modes)
+ * replaces  utils/flow_utils.py:153-190  forwardWarp.forward  (sign = -1)
+ *           utils/flow_utils.py:83-120   backWarp.forward     (sign = +1)
+ *           utils/flow_utils.py:212-221  FrameWarp.warp_frame
+ * ------------------------------------------------------------------------- */
+/*
+ * img   [B, C, H, W];  out [B, C, H, W];  flow [B, 2, flowH, flowW], ch0 = u (x).
+ * flowH == H && flowW == W : flow is used as is.
+ * H == flowH/2 && W == flowW/2 (integer division) : the x0.5 bilinear
+ *   align_corners=True down-sampling of e2v/e2v_model.py:190 is fused into the
+ *   kernel (flow values are NOT rescaled, as in the reference).
+ * Sample position ((x + sign*u) * (W-1)/W, (y + sign*v) * (H-1)/H) -- the
+ * reference's 2*(x/W-0.5) normalisation under align_corners=True -- reflected
+ * about [0, W-1] x [0, H-1] (padding_mode='reflection').
+ */
+CF_API int cf_warp(const float *img, const float *flow, float *out, int B, int C, int H, int W,
+            int flowH, int flowW, float sign, cf_stream_t stream);
+
+/* The per-frame step of e2v/e2v_model.py:188-191 in one launch: warps the
+ * previous reconstruction img [B,Ci,H,W] with the full-resolution flow and the
+ * sparse codes [B,Cz,H/2,W/2] with the fused half-resolution flow. */
+CF_API int cf_warp_frame_and_codes(const float *img, const float *codes, const float *flow,
+                            float *img_out, float *codes_out, int B, int Ci, int Cz,
+                            int H, int W, float sign, cf_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Part 3: all-pairs correlation volume, pyramid and lookup
+ * replaces  ERAFT/corr.py:13-27,52-60  CorrBlock.__init__ / CorrBlock.corr
+ *           ERAFT/corr.py:29-50        CorrBlock.__call__
+ *           DCEIFlow/core/corr/raft_corr.py:16-65 (identical maths)
+ * ------------------------------------------------------------------------- */
+typedef enum cf_corr_precision {
+    CF_CORR_TF32 = 0, /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (default)  */
+    CF_CORR_FP32 = 1, /* SIMT FFMA, fp32 operands (reference arithmetic)             */
+    CF_CORR_3XTF32 = 2 /* tcgen05, 3-term split: ~fp32 accuracy at 3x the MMA work   */
+} cf_corr_precision;
+
+#define CF_CORR_MAX_LEVELS 6
+
+/*
+ * fmap1, fmap2  [B, D, h, w];  pyramid[l]  [B*h*w, 1, h>>l, w>>l]  (host array of
+ * `levels` device pointers).  pyramid[0][b*N+i, 0, y, x] =
+ * <fmap1[b,:,i], fmap2[b,:,y*w+x]> / sqrt(D); level l+1 = avg_pool2d(level l, 2, 2)
+ * (odd sizes are floored).
+ */
+CF_API size_t cf_corr_workspace_bytes(int B, int D, int h, int w, int levels, int precision);
+CF_API int cf_corr_build(const float *fmap1, const float *fmap2, int B, int D, int h, int w,
+                  int levels, float *const *pyramid, int precision,
+                  void *workspace, size_t workspace_bytes, cf_stream_t stream);
+
+/*
+ * coords [B, 2, h, w] (ch0 = x, ch1 = y, level-0 feature-map pixels);
+ * out [B, levels*(2r+1)^2, h, w]; channel l*(2r+1)^2 + i*(2r+1) + j is level l
+ * sampled bilinearly (zero outside) at (x/2^l + i - r, y/2^l + j - r): i runs
+ * along X -- the reference's transposed window (ERAFT/corr.py:37-43).
+ */
+CF_API int cf_corr_lookup(const float *const *pyramid, const float *coords, int B, int h, int w,
+                   int levels, int radius, float *out, cf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CISTAFLOW_H_ */
