@@ -2,11 +2,16 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace cf {
 
 static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -67,5 +72,7 @@ int cf_version(void) { return CISTAFLOW_VERSION; }
 const char *cf_last_error(void) { return cf::g_err; }
 
 int cf_device_check(void) { return cf::check_device(); }
+
+int64_t cf_launch_count(void) { return cf::g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -55,6 +55,10 @@ CF_API int cf_version(void);
 CF_API const char *cf_last_error(void);
 /* CF_OK when the CURRENT device can run the kernels (compute capability 10.x). */
 CF_API int cf_device_check(void);
+/* Number of CUDA kernels this library has launched (or recorded into a graph
+ * capture) in this process so far; benchmarks report it as evidence that the
+ * hand-written kernels -- not a fallback -- did the work. */
+CF_API int64_t cf_launch_count(void);
 
 /* ------------------------------------------------------------------------- *
  * Part 1: event stream -> voxel grid (+ normalisation)

@@ -1,0 +1,327 @@
+"""Parity of the CUDA path (libcistaflow.so through the Python mirror) with the
+oracle and with the reference-generated golden fixtures.  GPU only.
+
+Tolerances (BASELINE.json north_star):
+  voxel   bit-exact in deterministic mode; |err| <= 1e-5*(|ref|+1) in atomic mode
+  warp    |err| <= 1e-4 absolute
+  corr    1e-3 relative, measured normwise: max|err| <= 1e-3 * max|ref|
+          (element-wise relative error is meaningless for near-zero correlations,
+          SURVEY.md H3); the fp32 SIMT path is held to 1e-5 * max|ref|
+  lookup  on an identical pyramid: |err| <= 1e-4 * max|ref| (same gather, fp32)
+"""
+import numpy as np
+import pytest
+import torch
+
+import cistaflow_b200 as cf
+from cistaflow_b200 import synth
+from oracle import explicit, ref_port
+
+pytestmark = pytest.mark.gpu
+
+
+def dev_t(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_voxel_close(got, ref):
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    tol = 1e-5 * (np.abs(ref.astype(np.float64)) + 1.0)
+    assert (err <= tol).all(), f"max err {err.max():.3e}"
+
+
+# ------------------------------------------------------------------ voxel ---
+VOXEL_CASES = ["base", "dense_hot", "single", "two_same_t", "empty"]
+
+
+@pytest.mark.parametrize("case", VOXEL_CASES)
+def test_voxel_golden_deterministic_bit_exact(golden, cuda_device, case):
+    g = golden("voxel")
+    ev = g[f"{case}/events"]
+    nb, w, h = (int(v) for v in g[f"{case}/dims"])
+    got_t = cf.events_to_voxel_grid_pytorch(dev_t(ev, cuda_device), nb, w, h, mode="deterministic")
+    assert got_t.device.type == "cuda" and got_t.dtype == torch.float32 and got_t.shape == (nb, h, w)
+    assert np.array_equal(bits(got_t.cpu().numpy()), bits(g[f"{case}/torch"]))
+    got_n = cf.events_to_voxel_grid(ev.copy(), nb, w, h, mode="deterministic")
+    assert isinstance(got_n, np.ndarray) and got_n.dtype == np.float32
+    assert np.array_equal(bits(got_n), bits(g[f"{case}/numpy"]))
+    got_p = cf.events_to_voxel_grid_pol(ev.copy(), nb, w, h, mode="deterministic")
+    assert got_p.shape == (nb, 2, h, w)
+    assert np.array_equal(bits(got_p), bits(g[f"{case}/pol"]))
+
+
+@pytest.mark.parametrize("case", VOXEL_CASES)
+def test_voxel_golden_atomic(golden, cuda_device, case):
+    g = golden("voxel")
+    ev = g[f"{case}/events"]
+    nb, w, h = (int(v) for v in g[f"{case}/dims"])
+    keep = ev.copy()
+    assert_voxel_close(cf.events_to_voxel_grid(ev, nb, w, h, mode="atomic"), g[f"{case}/numpy"])
+    assert np.array_equal(ev, keep), "inputs must not be mutated"
+    assert_voxel_close(cf.events_to_voxel_grid_pytorch(dev_t(ev, cuda_device), nb, w, h, mode="atomic").cpu().numpy(),
+                       g[f"{case}/torch"])
+    assert_voxel_close(cf.events_to_voxel_grid_pol(ev, nb, w, h, mode="atomic"), g[f"{case}/pol"])
+
+
+def test_voxel_cpu_tensor_round_trips_to_cpu(golden, cuda_device):
+    g = golden("voxel")
+    ev = torch.from_numpy(g["base/events"].copy())
+    out = cf.events_to_voxel_grid_pytorch(ev, 5, 40, 30, mode="deterministic")
+    assert out.device.type == "cpu"
+    assert np.array_equal(bits(out.numpy()), bits(g["base/torch"]))
+
+
+@pytest.mark.parametrize("case", ["base", "dense_hot", "empty"])
+@pytest.mark.parametrize("mode", ["std", "maxmin"])
+@pytest.mark.parametrize("hot", [False, True])
+def test_preprocess_golden(golden, cuda_device, case, mode, hot):
+    g = golden("voxel")
+    got = cf.event_preprocess(g[f"{case}/numpy"].copy(), mode, hot)
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got, g[f"{case}/pre_numpy_{mode}_{int(hot)}"], rtol=1e-5, atol=1e-5)
+    got_t = cf.event_preprocess_pytorch(dev_t(g[f"{case}/torch"], cuda_device), mode, hot)
+    np.testing.assert_allclose(got_t.cpu().numpy(), g[f"{case}/pre_torch_{mode}_{int(hot)}"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,h,w,batch", [(15000, 180, 240, 3), (50000, 260, 346, 2), (4097, 33, 47, 5)])
+@pytest.mark.parametrize("flavour", ["torch", "numpy"])
+def test_voxel_batched_vs_sequential_oracle(cuda_device, n, h, w, batch, flavour):
+    """Config-size windows: deterministic mode bit-exact vs the plain-C sequential
+    oracle; atomic mode within 1e-5; fused normalisation vs the explicit oracle."""
+    ev, off = synth.event_windows(batch, n, h, w, seed=77)
+    ev[off[1] + 10:off[1] + 15, 1:3] = [[-1, 0], [w, 0], [0, h], [0, -2], [w + 5, h + 5]]  # out of grid -> dropped
+    ev_d, off_d = dev_t(ev, cuda_device), dev_t(off, cuda_device)
+    fl = explicit.FLAVOUR_TORCH if flavour == "torch" else explicit.FLAVOUR_NUMPY
+    ref = []
+    for b in range(batch):
+        win = ev[off[b]:off[b + 1]]
+        ok = (win[:, 1] >= 0) & (win[:, 1] < w) & (win[:, 2] >= 0) & (win[:, 2] < h)
+        assert ok[0] and ok[-1]  # t0 / dT come from the window's first/last row: keep them in-grid
+        ref.append(explicit.voxel_grid_sequential(win[ok], 5, w, h, fl))
+    ref = np.stack(ref)
+    det = cf.events_to_voxel_grid_batched(ev_d, off_d, 5, w, h, flavour=flavour, mode="deterministic").cpu().numpy()
+    assert np.array_equal(bits(det), bits(ref))
+    det2 = cf.events_to_voxel_grid_batched(ev_d, off_d, 5, w, h, flavour=flavour, mode="deterministic").cpu().numpy()
+    assert np.array_equal(bits(det), bits(det2)), "deterministic mode must be run-to-run identical"
+    atom = cf.events_to_voxel_grid_batched(ev_d, off_d, 5, w, h, flavour=flavour, mode="atomic").cpu().numpy()
+    assert_voxel_close(atom, ref)
+    # fused std normalisation + hot-pixel filter
+    thr = (20.0 if flavour == "torch" else 25.0) / 5
+    fused = cf.events_to_voxel_grid_batched(ev_d, off_d, 5, w, h, normalize="std", filter_hot_pixel=True,
+                                            flavour=flavour, mode="deterministic").cpu().numpy()
+    for b in range(batch):
+        np.testing.assert_allclose(fused[b], explicit.preprocess(ref[b], "std", thr), rtol=1e-5, atol=1e-5)
+
+
+def test_voxel_is_reverse(cuda_device):
+    ev = synth.events(2000, 20, 24, 5)
+    got = cf.events_to_voxel_grid(ev, 5, 24, 20, is_reverse=True, mode="deterministic")
+    rev = ev[::-1].copy()
+    rev[:, 3] = -1.0
+    ref = explicit.voxel_grid_sequential(rev, 5, 24, 20, explicit.FLAVOUR_NUMPY)
+    assert np.array_equal(bits(got), bits(ref))
+
+
+def test_voxel_full_size_properties(cuda_device):
+    """HS-ERGB scale (config 4): 1 M events at 624x970 -- properties that do not
+    need the sequential oracle: polarity sum is conserved, and atomic ~ deterministic."""
+    n, h, w = 1_000_000, 624, 970
+    ev = synth.events(n, h, w, seed=synth.seed_for(4))
+    ev_d = dev_t(ev, cuda_device)
+    off = torch.tensor([0, n], dtype=torch.int64, device=cuda_device)
+    det = cf.events_to_voxel_grid_batched(ev_d, off, 5, w, h, flavour="torch", mode="deterministic")
+    atom = cf.events_to_voxel_grid_batched(ev_d, off, 5, w, h, flavour="torch", mode="atomic")
+    pol = np.where(ev[:, 3] == 0, -1.0, 1.0).sum()
+    assert abs(det.double().sum().item() - pol) < 1e-2 * np.sqrt(n)   # each event deposits exactly its polarity
+    assert_voxel_close(atom.cpu().numpy(), det.cpu().numpy())
+    norm = cf.events_to_voxel_grid_batched(ev_d, off, 5, w, h, normalize="std", flavour="torch", mode="atomic")
+    nz = norm[norm != 0].double()
+    assert abs(nz.mean().item()) < 1e-3 and abs(nz.std(unbiased=False).item() - 1.0) < 1e-3
+
+
+def test_voxel_error_paths(cuda_device):
+    ev = dev_t(synth.events(10, 8, 8, 1), cuda_device)
+    with pytest.raises(AssertionError):
+        cf.events_to_voxel_grid_pytorch(ev[:, :3], 5, 8, 8)
+    with pytest.raises(AssertionError):
+        cf.events_to_voxel_grid_pytorch(ev, 0, 8, 8)
+    with pytest.raises(RuntimeError):
+        cf.events_to_voxel_grid_batched(ev.cpu(), torch.tensor([0, 10]), 5, 8, 8)
+
+
+# ------------------------------------------------------------------- warp ---
+def test_warp_golden(golden, cuda_device):
+    g = golden("warp")
+    img, flow = dev_t(g["img"], cuda_device), dev_t(g["flow"], cuda_device)
+    fw, bw = cf.forwardWarp(22, 18), cf.backWarp(22, 18)
+    np.testing.assert_allclose(fw(img, flow).cpu().numpy(), g["forward"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(bw(img, flow).cpu().numpy(), g["backward"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(fw(img, torch.zeros_like(flow)).cpu().numpy(), g["zero_flow_forward"], rtol=0, atol=1e-4)
+
+
+def test_warp_frame_and_codes_golden(golden, cuda_device):
+    g = golden("warp")
+    img, codes, flow = (dev_t(g[f"step/{k}"], cuda_device) for k in ("img", "codes", "flow"))
+    frame = cf.FrameWarp("forward")
+    np.testing.assert_allclose(frame.warp_frame(img, flow).cpu().numpy(), g["step/img_warped"], rtol=0, atol=1e-4)
+    half = dev_t(g["step/flow_half"], cuda_device)
+    np.testing.assert_allclose(frame.warp_frame(codes, half).cpu().numpy(), g["step/codes_warped"], rtol=0, atol=1e-4)
+    # fused x0.5 down-sampling: pass the full-resolution flow with the half-resolution codes
+    np.testing.assert_allclose(cf.warp(codes, flow, -1.0).cpu().numpy(), g["step/codes_warped"], rtol=0, atol=1e-4)
+    wi, wz = cf.warp_frame_and_codes(img, codes, flow, "forward")
+    np.testing.assert_allclose(wi.cpu().numpy(), g["step/img_warped"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(wz.cpu().numpy(), g["step/codes_warped"], rtol=0, atol=1e-4)
+    _, wzb = cf.FrameWarp("backward").warp_frame_and_codes(img, codes, flow)
+    np.testing.assert_allclose(wzb.cpu().numpy(), g["step/codes_warped_backward"], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("h,w,batch,channels", [(180, 240, 2, 128), (260, 346, 1, 128), (90, 120, 3, 5), (17, 23, 2, 1)])
+@pytest.mark.parametrize("mode", ["forward", "backward"])
+def test_warp_vs_oracle_config_shapes(cuda_device, h, w, batch, channels, mode):
+    """Codes-shaped inputs (C=128 at H/2 x W/2) and image-shaped ones against the
+    library-call oracle (F.grid_sample on CPU)."""
+    img, codes, flow = synth.warp_inputs(batch, h, w, seed=5, code_channels=channels, flow_sigma=6.0)
+    ref_i, ref_z = ref_port.warp_frame_and_codes(torch.from_numpy(img), torch.from_numpy(codes), torch.from_numpy(flow), mode)
+    wi, wz = cf.warp_frame_and_codes(dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(flow, cuda_device), mode)
+    assert (wi.cpu() - ref_i).abs().max().item() <= 1e-4
+    assert (wz.cpu() - ref_z).abs().max().item() <= 1e-4
+    frame = cf.FrameWarp(mode)
+    assert (frame.warp_frame(dev_t(img, cuda_device), dev_t(flow, cuda_device)).cpu() - ref_i).abs().max().item() <= 1e-4
+
+
+def test_warp_full_size_properties(cuda_device):
+    """480x640 codes (config 5): constant image stays constant (weights sum to 1);
+    linearity warp(a*x + y) = a*warp(x) + warp(y); forward(flow) == backward(-flow)."""
+    B, C, H, W = 2, 128, 240, 320
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(B, C, H, W, generator=gen).to(cuda_device)
+    y = torch.randn(B, C, H, W, generator=gen).to(cuda_device)
+    flow = (7.0 * torch.randn(B, 2, 2 * H, 2 * W, generator=gen)).to(cuda_device)
+    const = torch.full_like(x, 3.25)
+    assert (cf.warp(const, flow, -1.0) - 3.25).abs().max().item() <= 1e-5
+    lhs = cf.warp(2.5 * x + y, flow, -1.0)
+    rhs = 2.5 * cf.warp(x, flow, -1.0) + cf.warp(y, flow, -1.0)
+    assert (lhs - rhs).abs().max().item() <= 1e-4
+    assert torch.equal(cf.warp(x, flow, -1.0), cf.warp(x, -flow, +1.0))
+
+
+def test_warp_rejects_cpu_and_grad(cuda_device):
+    img = torch.zeros(1, 1, 8, 8)
+    with pytest.raises(RuntimeError):
+        cf.forwardWarp(8, 8)(img, torch.zeros(1, 2, 8, 8))
+    g = torch.zeros(1, 1, 8, 8, device=cuda_device, requires_grad=True)
+    with pytest.raises(RuntimeError):
+        cf.forwardWarp(8, 8)(g, torch.zeros(1, 2, 8, 8, device=cuda_device))
+    with pytest.raises(ValueError):
+        cf.warp(torch.zeros(1, 1, 8, 8, device=cuda_device), torch.zeros(1, 2, 5, 5, device=cuda_device), -1.0)
+
+
+# ------------------------------------------------------------------- corr ---
+def corr_err(got, ref):
+    return float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() / max(np.abs(ref).max(), 1e-30))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+def test_corr_golden(golden, cuda_device, precision, tol):
+    g = golden("corr")
+    blk = cf.CorrBlock(dev_t(g["fmap1"], cuda_device), dev_t(g["fmap2"], cuda_device), num_levels=4, radius=4,
+                       precision=precision)
+    assert len(blk.corr_pyramid) == 4
+    for l in range(4):
+        assert tuple(blk.corr_pyramid[l].shape) == g[f"pyr{l}"].shape
+        assert corr_err(blk.corr_pyramid[l].cpu().numpy(), g[f"pyr{l}"]) <= tol, f"level {l}"
+    out = blk(dev_t(g["coords"], cuda_device))
+    assert tuple(out.shape) == g["lookup"].shape and out.is_contiguous()
+    assert corr_err(out.cpu().numpy(), g["lookup"]) <= tol
+    vol = cf.CorrBlock.corr(dev_t(g["fmap1"], cuda_device), dev_t(g["fmap2"], cuda_device), precision=precision)
+    assert tuple(vol.shape) == (1, 16, 24, 1, 16, 24)
+
+
+def test_corr_golden_odd_sizes(golden, cuda_device):
+    """15x20 maps, 3 levels, radius 3: avg_pool floors, runtime-radius lookup kernel."""
+    g = golden("corr")
+    blk = cf.CorrBlock(dev_t(g["odd/fmap1"], cuda_device), dev_t(g["odd/fmap2"], cuda_device), num_levels=3, radius=3,
+                       precision="fp32")
+    for l in range(3):
+        assert tuple(blk.corr_pyramid[l].shape) == g[f"odd/pyr{l}"].shape
+        assert corr_err(blk.corr_pyramid[l].cpu().numpy(), g[f"odd/pyr{l}"]) <= 1e-5
+    assert corr_err(blk(dev_t(g["odd/coords"], cuda_device)).cpu().numpy(), g["odd/lookup"]) <= 1e-5
+    blk_tc = cf.CorrBlock(dev_t(g["odd/fmap1"], cuda_device), dev_t(g["odd/fmap2"], cuda_device), num_levels=3, radius=3,
+                          precision="tf32")  # 15x20: N % 4 == 0, odd h -> un-fused tensor-core path
+    for l in range(3):
+        assert corr_err(blk_tc.corr_pyramid[l].cpu().numpy(), g[f"odd/pyr{l}"]) <= 1e-3
+
+
+def test_lookup_on_reference_pyramid(golden, cuda_device):
+    """Feed the REFERENCE's pyramid to our lookup: isolates the gather from the GEMM."""
+    g = golden("corr")
+    pyr = [dev_t(g[f"pyr{l}"], cuda_device) for l in range(4)]
+    out = cf.corr_lookup(pyr, dev_t(g["coords"], cuda_device), 4)
+    assert corr_err(out.cpu().numpy(), g["lookup"]) <= 1e-4
+    assert np.abs(out.cpu().numpy()[0, :, 0, 0]).max() == 0.0  # query far outside: zero padding everywhere
+
+
+@pytest.mark.parametrize("h,w,batch", [(180, 240, 8), (260, 346, 1), (480, 640, 1)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+def test_corr_vs_oracle_config_shapes(cuda_device, h, w, batch, precision, tol):
+    f1, f2, coords = synth.corr_inputs(batch, h, w, seed=9)
+    ref_pyr = ref_port.corr_pyramid(torch.from_numpy(f1), torch.from_numpy(f2), 4)
+    blk = cf.CorrBlock(dev_t(f1, cuda_device), dev_t(f2, cuda_device), precision=precision)
+    for l in range(4):
+        assert tuple(blk.corr_pyramid[l].shape) == tuple(ref_pyr[l].shape)
+        assert corr_err(blk.corr_pyramid[l].cpu().numpy(), ref_pyr[l].numpy()) <= tol, f"level {l}"
+    ref_out = ref_port.corr_lookup(ref_pyr, torch.from_numpy(coords), 4)
+    assert corr_err(blk(dev_t(coords, cuda_device)).cpu().numpy(), ref_out.numpy()) <= tol
+
+
+def test_corr_full_size_properties(cuda_device):
+    """624x970 (config 4: N = 9920, 394 MB level 0): symmetry corr(f1,f2)[i,j] ==
+    corr(f2,f1)[j,i] on a sample, level-1 == 2x2 mean of level 0, lookup at integer
+    coords with zero fraction returns the level-0 entries."""
+    f1, f2, _ = synth.corr_inputs(1, 624, 970, seed=4)
+    a, b = dev_t(f1, cuda_device), dev_t(f2, cuda_device)
+    h, w = a.shape[-2:]
+    N = h * w
+    blk = cf.CorrBlock(a, b, precision="tf32")
+    l0 = blk.corr_pyramid[0].view(N, h, w)
+    idx = torch.randint(0, N, (64,), device=cuda_device)
+    exact = (a[0].reshape(256, N)[:, idx].double().T @ b[0].reshape(256, N).double()) / 16.0
+    got = l0.view(N, N)[idx].double()
+    assert (got - exact).abs().max().item() <= 1e-3 * exact.abs().max().item()
+    pooled = torch.nn.functional.avg_pool2d(l0[idx], 2, 2)
+    assert (blk.corr_pyramid[1].view(N, h // 2, w // 2)[idx] - pooled).abs().max().item() <= 1e-5
+    coords = cf.coords_grid(1, h, w, device=cuda_device)
+    out = blk(coords)
+    centre = out[0, 4 * 9 + 4].reshape(N)          # level 0, i = j = r
+    assert torch.equal(centre, l0.view(N, N).diagonal())
+
+
+# ------------------------------------------------------------ model traces ---
+@pytest.mark.parametrize("trace", ["trace_eiflow", "trace_eraft"])
+def test_model_trace_replay(golden, cuda_device, trace):
+    """Every hot-path call the reference model made on its 3rd recurrent frame,
+    replayed through the CUDA path (real feature / flow statistics, ImagePadder shapes)."""
+    g = golden(trace)
+    H, W, nev, n_lookup, n_warp = (int(v) for v in g["meta"])
+    grid = cf.events_to_voxel_grid(g["voxel/events"], 5, W, H, mode="deterministic")
+    assert np.array_equal(bits(grid), bits(g["voxel/grid"]))
+    np.testing.assert_allclose(cf.event_preprocess(grid, "std", True), g["voxel/normalised"], rtol=1e-5, atol=1e-5)
+    blk = cf.CorrBlock(dev_t(g["corr/fmap1"], cuda_device), dev_t(g["corr/fmap2"], cuda_device), num_levels=4, radius=4)
+    for l in range(4):
+        assert corr_err(blk.corr_pyramid[l].cpu().numpy(), g[f"corr/pyr{l}"]) <= 1e-3
+    for k in range(n_lookup):
+        if f"lookup{k}/out" in g:
+            out = blk(dev_t(g[f"lookup{k}/coords"], cuda_device))
+            assert corr_err(out.cpu().numpy(), g[f"lookup{k}/out"]) <= 1e-3
+    frame = cf.FrameWarp("forward")
+    for k in range(n_warp):
+        out = frame.warp_frame(dev_t(g[f"warp{k}/in"], cuda_device), dev_t(g[f"warp{k}/flow"], cuda_device))
+        np.testing.assert_allclose(out.cpu().numpy(), g[f"warp{k}/out"], rtol=0, atol=1e-4)
+    wi, wz = cf.warp_frame_and_codes(dev_t(g["warp0/in"], cuda_device), dev_t(g["warp1/in"], cuda_device),
+                                     dev_t(g["flow_final"], cuda_device), "forward")
+    np.testing.assert_allclose(wi.cpu().numpy(), g["warp0/out"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(wz.cpu().numpy(), g["warp1/out"], rtol=0, atol=1e-4)
