@@ -9,12 +9,17 @@
 // GEMM view, per batch item b:   C[i, j] = sum_k A[k, i] * Bm[k, j]
 //   A = fmap1[b] (D x N), Bm = fmap2[b] (D x N), N = h*w contiguous: BOTH
 //   operands are "MN-major" (the reference's fmap1.transpose(1,2) is free).
-//   The tiles are loaded as TMA boxes of 32 (MN, 128 bytes) x 32 (K rows) which
-//   land in the canonical UMMA MN-major SWIZZLE_128B layout:
-//   ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units, LBO = 4096 B between
-//   32-column atoms (one TMA box each), SBO = 1024 B between groups of 8 K rows.
-//   One tcgen05.mma kind::tf32 has K = 8, i.e. consumes one 8-row group: the
-//   descriptor start address advances by 1024 B per MMA.
+//   The tiles are loaded as TMA boxes of 32 (MN, 128 bytes) x 32 (K rows) with
+//   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, which lands them in the only shared
+//   memory layout tcgen05 accepts for MN-major 32-bit operands: UMMA layout type
+//   1, "128B swizzle with 32-byte atoms" (Swizzle<2,5,2>: the 32-byte chunk index
+//   of a 128-byte row is XORed with row % 4).  Canonical form, in 16-byte units:
+//   ((8,n),(4,k)) : ((1,LBO),(8,SBO)) -- LBO = 4096 B between 32-column atoms
+//   (one TMA box each), SBO = 512 B between groups of 4 K rows.  One tcgen05.mma
+//   kind::tf32 has K = 8 = two 4-row groups, so the descriptor start address
+//   advances by 1024 B per MMA.  (The plain SWIZZLE_128B layout is silently
+//   computed as zeros for MN-major tf32; scripts/tc_probe.cu is the single-tile
+//   probe that established this on a B200.)
 //
 // Tile: 128 queries (M, TMEM lanes) x BN targets (TMEM columns).  With pooling
 // fused, BN = R*w covers R (even) whole rows of the target map so that each 2x2
@@ -146,14 +151,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, MN-major, SWIZZLE_128B (see file header)
+// UMMA shared-memory descriptor, MN-major, 128B swizzle with 32B atoms (see file header)
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address            bits [0,14)
     d |= (uint64_t)(4096u >> 4) << 16;               // leading byte offset (MN) bits [16,30)
-    d |= (uint64_t)(1024u >> 4) << 32;               // stride byte offset (K)   bits [32,46)
+    d |= (uint64_t)(512u >> 4) << 32;                // stride byte offset (K)   bits [32,46)
     d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    d |= (uint64_t)1 << 61;                          // layout type 1 = SWIZZLE_128B_BASE32B
     return d;
 }
 // instruction descriptor: D=f32, A=B=tf32, both MN-major, M=128, N=n
@@ -388,7 +393,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D map over a feature map viewed as [B*D rows, N cols], box 32 x 32, 128B swizzle
+// 2-D map over a feature map viewed as [B*D rows, N cols], box 32 x 32, 128B swizzle / 32B atoms
 static int make_fmap_tmap(CUtensorMap *m, const float *base, int B, int D, int N, CUtensorMapDataType dt) {
     EncodeTiledFn fn = encode_fn();
     CF_REQUIRE(fn, CF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
@@ -397,7 +402,7 @@ static int make_fmap_tmap(CUtensorMap *m, const float *base, int B, int D, int N
     cuuint32_t box[2] = {32, 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, dt, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return CF_OK;
 }
