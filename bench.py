@@ -47,7 +47,7 @@ sys.path.insert(0, ROOT)
 CFG = dict(workload="configs[1]: cista-eraft hot path, 180x240, 15000 ev/frame, batch 8, "
                     "CorrBlock 4 levels radius 4, 12 lookups/frame",
            H=180, W=240, batch=8, events=15000, bins=5, levels=4, radius=4, lookups=12, code_channels=128,
-           warp_mode="forward")
+           warp_mode="forward", flow_kind="smooth")
 N_SETS = 2  # rotating input/output sets; one set (in+out) is ~240 MB > 126 MB L2
 
 
@@ -57,7 +57,8 @@ def make_host_inputs(cfg, seed0):
     for s in range(N_SETS):
         seed = seed0 + 101 * s
         ev, off = synth.event_windows(cfg["batch"], cfg["events"], cfg["H"], cfg["W"], seed)
-        img, codes, flow = synth.warp_inputs(cfg["batch"], cfg["H"], cfg["W"], seed + 1, cfg["code_channels"])
+        img, codes, flow = synth.warp_inputs(cfg["batch"], cfg["H"], cfg["W"], seed + 1, cfg["code_channels"],
+                                             flow_kind=cfg["flow_kind"])
         f1, f2, c0 = synth.corr_inputs(cfg["batch"], cfg["H"], cfg["W"], seed + 2)
         rng = np.random.default_rng(seed + 3)
         coords = [c0] + [(c0 + 0.5 * rng.standard_normal(c0.shape)).astype(np.float32) for _ in range(cfg["lookups"] - 1)]
@@ -383,7 +384,7 @@ def run_ours(args, cfg):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 event time, tf32 correlation)",
         "data": "synthetic",
-        "config": {**{k: cfg[k] for k in ("workload", "H", "W", "batch", "events", "lookups")},
+        "config": {**{k: cfg[k] for k in ("workload", "H", "W", "batch", "events", "lookups", "flow_kind")},
                    "streams_total": frames, "parallelism": f"{world} x 8 independent streams, no data-path collective",
                    "timing": f"step = 1 CUDA-graph replay; {N_SETS} rotating input/output sets, "
                              f"~{(sum(model[k] for k in ('voxel', 'warp', 'corr_build_bytes')) + 12 * model['lookup']) / 1e6:.0f} MB "

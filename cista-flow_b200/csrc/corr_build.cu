@@ -102,6 +102,42 @@ avg_pool2x2_kernel(const float *__restrict__ in, float *__restrict__ out, int64_
     }
 }
 
+// level l+1 AND level l+2 from level l in one launch (the two smallest pyramid levels): one thread
+// per 2x2 group of level-(l+1) cells; floor semantics on odd sizes are kept exactly.
+__global__ void __launch_bounds__(256)
+avg_pool_two_levels_kernel(const float *__restrict__ in, float *__restrict__ out1, float *__restrict__ out2, int64_t groups,
+                           int Hi, int Wi, int H1, int W1, int H2, int W2) {
+    const int GH = (H1 + 1) / 2, GW = (W1 + 1) / 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        const int X = (int)(g % GW);
+        const int64_t t = g / GW;
+        const int Y = (int)(t % GH);
+        const int64_t m = t / GH;
+        float v[2][2] = {};
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int y1 = 2 * Y + dy, x1 = 2 * X + dx;
+                if (y1 < H1 && x1 < W1) {
+                    const float *p = in + (m * Hi + 2 * y1) * Wi + 2 * x1;
+                    float s = __ldg(p) + __ldg(p + 1);
+                    s += __ldg(p + Wi);
+                    s += __ldg(p + Wi + 1);
+                    v[dy][dx] = s / 4.f;
+                    out1[(m * H1 + y1) * W1 + x1] = v[dy][dx];
+                }
+            }
+        if (Y < H2 && X < W2) {
+            float s = v[0][0] + v[0][1];
+            s += v[1][0];
+            s += v[1][1];
+            out2[(m * H2 + Y) * W2 + X] = s / 4.f;
+        }
+    }
+}
+
 }  // namespace cf
 
 extern "C" size_t cf_corr_workspace_bytes(int B, int D, int h, int w, int, int precision) {
@@ -145,6 +181,16 @@ extern "C" int cf_corr_build(const float *fmap1, const float *fmap2, int B, int 
         if (fused) first_pooled = 2;
     }
     for (int l = first_pooled; l < levels; ++l) {
+        if (l + 1 < levels) {  // two levels per launch
+            const int Hi = h >> (l - 1), Wi = w >> (l - 1), H1 = h >> l, W1 = w >> l, H2 = h >> (l + 1), W2 = w >> (l + 1);
+            const int64_t groups = (int64_t)B * N * ((H1 + 1) / 2) * ((W1 + 1) / 2);
+            const int64_t blocks = ceil_div(groups, 256);
+            const unsigned g = (unsigned)(blocks < (int64_t)148 * 32 ? blocks : (int64_t)148 * 32);
+            avg_pool_two_levels_kernel<<<g, 256, 0, stream>>>(pyramid[l - 1], pyramid[l], pyramid[l + 1], groups, Hi, Wi, H1, W1, H2, W2);
+            CF_LAUNCH_CHECK("avg_pool_two_levels_kernel");
+            ++l;
+            continue;
+        }
         const int Hi = h >> (l - 1), Wi = w >> (l - 1), Ho = h >> l, Wo = w >> l;
         const int64_t total = (int64_t)B * N * Ho * Wo;
         const int64_t blocks = ceil_div(total, 256);

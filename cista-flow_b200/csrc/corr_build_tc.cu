@@ -29,17 +29,19 @@
 // never re-read: the volume is HBM-write bound (96 FLOP/B).
 //
 // Persistent, warp-specialised CTA (1 per SM, 192 threads):
-//   warps 0-3  epilogue (TMEM lane quarter = warp id), TMEM -> registers -> global
+//   warps 0-3  epilogue (TMEM lane quarter = warp id): TMEM -> registers -> swizzled smem -> TMA store
 //   warp  4    TMA producer (one elected lane)
 //   warp  5    TMEM allocator + MMA issuer (one elected lane)
 // Two TMEM accumulator stages (2 x 256 columns) let the MMA of tile t+1 overlap
 // the epilogue of tile t; a 4-stage shared-memory ring feeds the MMA.
 //
 // Operand precision: tcgen05 kind::tf32 reads fp32 words and ignores the low 13
-// mantissa bits (truncation), which biases every product low by ~1e-3 relative.
-// A pre-pass rounds the feature maps to TF32 with round-to-nearest
-// (cvt.rna.tf32.f32) into the workspace, making the error unbiased
-// (max |err| ~ 3e-4 * max|ref| at D=256, within the 1e-3 gate).
+// mantissa bits (truncation), which biases every product low (measured: signed
+// relative bias -7e-4, max|err| 7.7e-4*max|ref| at D=256).  Encoding the tensor
+// maps with CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 makes the TMA unit round the
+// operands to TF32 (nearest) on their way into shared memory -- measured
+// identical to a cvt.rna.tf32.f32 pre-pass: bias -5e-7, max|err| 2.8e-4*max|ref|
+// -- so no extra pass over the feature maps and no workspace are needed.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -56,7 +58,9 @@ constexpr int BOX_BYTES = 32 * 32 * 4;                 // one TMA box: 32 cols x
 constexpr int A_BYTES = (BM / 32) * BOX_BYTES;         // 16 KB
 constexpr int B_BYTES = (MAX_BN / 32) * BOX_BYTES;     // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;         // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_BUF_BYTES = 32 * 32 * 4;               // one 32x32 fp32 output box, 128B swizzle
+constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*double buffer*/ * EPI_BUF_BYTES;  // 32 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;  // ~seconds; a stuck pipeline traps instead of hanging the GPU
 
@@ -117,6 +121,19 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, int
         : "memory");
 }
 
+// smem (32 rows x 128 B, 128B swizzle) -> global box {32 cols, 32 rows, 1} of the [B][N][N] volume
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N committed store groups may still be READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -167,6 +184,12 @@ __host__ __device__ inline uint32_t make_idesc_tf32(int n) {
            ((uint32_t)(BM >> 4) << 24);
 }
 
+// Debug timeline of CTA 0's first tile (clock64 stamps), read back with cf_debug_tc_timeline().
+__device__ unsigned long long g_tc_timeline[32];
+__device__ __forceinline__ void stamp(int slot) {
+    if (blockIdx.x == 0) g_tc_timeline[slot] = (unsigned long long)clock64();
+}
+
 __device__ __forceinline__ void decode_tile(const Params &p, int tile, int &b, int &mb, int &nb) {
     nb = tile % p.tiles_n;
     const int t = tile / p.tiles_n;
@@ -203,20 +226,24 @@ __device__ __forceinline__ void store_row_chunk(float *dst, const uint32_t (&v)[
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint8_t *epi = smem + STAGES * STAGE_BYTES;  // [4 warps][2][EPI_BUF_BYTES]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi + EPI_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES;
     uint64_t *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = p.D / BK;
+    if (threadIdx.x == 0) stamp(0);
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        tma_prefetch_desc(&tmap_c);
     }
     if (warp == 5) {
         if (lane == 0) {
@@ -231,6 +258,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) stamp(1);
 
     if (warp == 4) {
         // ------------------------------------------------------------ TMA producer
@@ -250,6 +278,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int a = 0; a < BM / 32; ++a) tma_load_2d(sa + a * BOX_BYTES, &tmap_a, i0 + 32 * a, krow, &full[stage]);
                     for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOX_BYTES, &tmap_b, j0 + 32 * a, krow, &full[stage]);
+                    if (tile == (int)blockIdx.x && kb == 0) stamp(2);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -267,6 +296,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
+                    if (tile == (int)blockIdx.x && kb < 16) stamp(3 + kb);
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk)
@@ -276,6 +306,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+                if (tile == (int)blockIdx.x) stamp(19);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -283,10 +314,11 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else {
         // ---------------------------------------------------------------- epilogue
         int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, chunk_count = 0;
         const int row = 32 * warp + lane;
         const bool vec4_l0 = (p.N % 4) == 0 && (p.w % 4) == 0;
         const bool vec4_l1 = (p.w1 % 4) == 0;
+        uint8_t *my_epi = epi + warp * 2 * EPI_BUF_BYTES;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int b, mb, nb;
             decode_tile(p, tile, b, mb, nb);
@@ -294,18 +326,48 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const bool row_ok = i < p.N;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            if (tile == (int)blockIdx.x && threadIdx.x == 0) stamp(20);
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)acc * MAX_BN;
-            float *l0row = p.l0 + ((size_t)b * p.N + (row_ok ? i : 0)) * p.N;
-            if (p.R == 0) {
-                const int j0 = nb * p.BN;
-                for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            const int j0 = nb * p.BN;
+            const int bn_valid = min(p.BN, p.N - j0);  // accumulator column c <-> target index j0 + c
+            // ---- level 0: TMEM -> registers (x scale) -> swizzled smem box -> TMA bulk store.
+            // A warp-wide st.global of this fragment would touch 32 different rows per instruction
+            // (measured: 18k cycles per tile); the TMA writes whole 128-byte lines instead.
+            if (bn_valid >= 32) {
+                const int nchunks = (bn_valid + 31) / 32;
+                for (int ci = 0; ci < nchunks; ++ci) {
+                    const int c0 = min(ci * 32, bn_valid - 32);  // last chunk overlaps its neighbour (same values)
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
-                    int nvalid = min(32, min(p.BN - c0, p.N - (j0 + c0)));
-                    if (row_ok && nvalid > 0) store_row_chunk(l0row + j0 + c0, v, p.scale, nvalid, vec4_l0 && (nvalid % 4 == 0), p.stream_l0 != 0);
+                    uint8_t *buf = my_epi + (chunk_count & 1) * EPI_BUF_BYTES;
+                    if (chunk_count >= 2) {  // the store issued two chunks ago has finished reading this buffer
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 o = make_float4(__uint_as_float(v[4 * q]) * p.scale, __uint_as_float(v[4 * q + 1]) * p.scale,
+                                                     __uint_as_float(v[4 * q + 2]) * p.scale, __uint_as_float(v[4 * q + 3]) * p.scale);
+                        *reinterpret_cast<float4 *>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tmap_c, buf, j0 + c0, mb * BM + 32 * warp, b);
+                        tma_store_commit();
+                    }
+                    ++chunk_count;
                 }
             } else {
+                float *l0row = p.l0 + ((size_t)b * p.N + (row_ok ? i : 0)) * p.N;
+                uint32_t v[32];
+                tmem_ld32(taddr, v);
+                tmem_ld_wait();
+                if (row_ok && bn_valid > 0) store_row_chunk(l0row + j0, v, p.scale, bn_valid, vec4_l0 && (bn_valid % 4 == 0), false);
+            }
+            // ---- level 1: 2x2 means straight from the accumulator rows
+            if (p.R != 0) {
                 const int y0 = nb * p.R;
                 float *l1map = p.l1 + ((size_t)b * p.N + (row_ok ? i : 0)) * p.h1 * p.w1;
                 for (int pr = 0; pr < p.R; pr += 2) {
@@ -316,10 +378,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         tmem_ld32(taddr + pr * p.w + xc, ra);
                         tmem_ld32(taddr + (pr + 1) * p.w + xc, rc);
                         tmem_ld_wait();
-                        const int nvalid = min(32, p.w - xc);
                         if (row_ok) {
-                            store_row_chunk(l0row + (size_t)y * p.w + xc, ra, p.scale, nvalid, vec4_l0, p.stream_l0 != 0);
-                            store_row_chunk(l0row + (size_t)(y + 1) * p.w + xc, rc, p.scale, nvalid, vec4_l0, p.stream_l0 != 0);
                             // ATen avg_pool2d: ((a + b) + c) + d, then / 4, on the stored (scaled) values
                             float *dst = l1map + (size_t)(y >> 1) * p.w1 + (xc >> 1);
                             const int npool = min(16, p.w1 - (xc >> 1));
@@ -347,33 +406,19 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
+            if (tile == (int)blockIdx.x && threadIdx.x == 0) stamp(21);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
     }
+    if (warp < 4 && lane == 0) tma_store_wait_all();  // bulk stores must drain before the CTA's smem goes away
     tc_fence_before();
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
-}
-
-// fp32 -> tf32 round-to-nearest (ties away), 4 elements per thread
-__global__ void __launch_bounds__(256) tf32_round_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b,
-                                                         float4 *__restrict__ oa, float4 *__restrict__ ob, int64_t n4) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n4; i += stride) {
-        const bool second = i >= n4;
-        const int64_t k = second ? i - n4 : i;
-        float4 v = __ldg((second ? b : a) + k);
-        uint32_t x, y, z, w;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x) : "f"(v.x));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(v.y));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(z) : "f"(v.z));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(w) : "f"(v.w));
-        (second ? ob : oa)[k] = make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(w));
-    }
+    if (threadIdx.x == 0) stamp(22);
 }
 
 // ---- host side --------------------------------------------------------------------
@@ -407,40 +452,38 @@ static int make_fmap_tmap(CUtensorMap *m, const float *base, int B, int D, int N
     return CF_OK;
 }
 
+// 3-D map over the level-0 volume [B][N][N], box {32 cols, 32 rows, 1}, 128B swizzle (store side)
+static int make_volume_tmap(CUtensorMap *m, float *base, int B, int N) {
+    EncodeTiledFn fn = encode_fn();
+    CF_REQUIRE(fn, CF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)N * sizeof(float), (cuuint64_t)N * N * sizeof(float)};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_CUDA, "cuTensorMapEncodeTiled (volume) failed with CUresult %d", (int)r);
+    return CF_OK;
+}
+
 }  // namespace tc
 
 bool corr_tensor_core_supported(int D, int h, int w) {
     return D % tc::BK == 0 && ((int64_t)h * w) % 4 == 0;
 }
 
-size_t corr_tc_workspace_bytes(int B, int D, int h, int w) {
-    return 2 * align_up((size_t)B * D * h * w * sizeof(float), 256);
-}
+size_t corr_tc_workspace_bytes(int, int, int, int) { return 0; }
 
-// flags (debug/experiments, env CF_TC_FLAGS): bit0 = skip the RN pre-pass (feed raw fp32, hardware truncation),
-// bit1 = encode the tensor maps as TFLOAT32 instead of FLOAT32, bit2 = never fuse the pooling.
+// flags (debug/experiments, env CF_TC_FLAGS): bit1 = encode the tensor maps as plain FLOAT32 (operands are
+// then truncated, not rounded, to TF32), bit2 = never fuse the pooling.
 int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int h, int w, float scale, float *level0,
-                            float *level1, int precision, void *ws, size_t ws_bytes, int flags, int *fused_level1,
+                            float *level1, int precision, void *, size_t, int flags, int *fused_level1,
                             cudaStream_t stream) {
     using namespace tc;
     CF_REQUIRE(precision == CF_CORR_TF32, CF_ERR_UNSUPPORTED, "cf_corr_build: CF_CORR_3XTF32 is not implemented yet");
     CF_REQUIRE(aligned16(f1) && aligned16(f2) && aligned16(level0), CF_ERR_ALIGN, "cf_corr_build: tensors must be 16-byte aligned");
     const int N = h * w;
     const float *a = f1, *bm = f2;
-    if (!(flags & 1)) {
-        const size_t half = align_up((size_t)B * D * N * sizeof(float), 256);
-        CF_REQUIRE(ws && ws_bytes >= 2 * half, CF_ERR_WORKSPACE, "cf_corr_build: workspace too small (%zu < %zu)", ws_bytes, 2 * half);
-        CF_REQUIRE(aligned16(ws), CF_ERR_ALIGN, "cf_corr_build: workspace not 16-byte aligned");
-        float *ra = reinterpret_cast<float *>(ws), *rb = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + half);
-        const int64_t n4 = (int64_t)B * D * N / 4;
-        const int64_t blocks = ceil_div(2 * n4, 256);
-        tf32_round_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(
-            reinterpret_cast<const float4 *>(f1), reinterpret_cast<const float4 *>(f2), reinterpret_cast<float4 *>(ra),
-            reinterpret_cast<float4 *>(rb), n4);
-        CF_LAUNCH_CHECK("tf32_round_kernel");
-        a = ra;
-        bm = rb;
-    }
     Params p{};
     p.B = B; p.D = D; p.N = N; p.h = h; p.w = w; p.scale = scale; p.l0 = level0; p.l1 = level1;
     p.h1 = h / 2; p.w1 = w / 2;
@@ -470,10 +513,11 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     CF_REQUIRE(total < (1ll << 31), CF_ERR_INVALID_ARG, "cf_corr_build: too many tiles");
     p.total_tiles = (int)total;
 
-    const CUtensorMapDataType dt = (flags & 2) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    CUtensorMap ta, tb;
+    const CUtensorMapDataType dt = (flags & 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+    CUtensorMap ta, tb, tcm;
     if (int rc = make_fmap_tmap(&ta, a, B, D, N, dt)) return rc;
     if (int rc = make_fmap_tmap(&tb, bm, B, D, N, dt)) return rc;
+    if (int rc = make_volume_tmap(&tcm, level0, B, N)) return rc;
 
     int dev = 0;
     CF_CUDA(cudaGetDevice(&dev));
@@ -483,9 +527,14 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         opt_in[dev & 63] = true;
     }
     const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    corr_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+    corr_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, tcm, p);
     CF_LAUNCH_CHECK("corr_tc_kernel");
     return CF_OK;
 }
 
 }  // namespace cf
+
+// debug only (not part of include/cistaflow.h): copies the 32 clock64 stamps of the last launch
+extern "C" __attribute__((visibility("default"))) int cf_debug_tc_timeline(unsigned long long *host_out) {
+    return cudaMemcpyFromSymbol(host_out, cf::tc::g_tc_timeline, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -6;
+}

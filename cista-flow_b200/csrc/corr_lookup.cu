@@ -15,12 +15,18 @@
 // built).  Algorithmic bytes per query: 4*L*(2r+1)^2 written + 8 read (coords)
 // + 4*L*(2r+2)^2 read (patches) = 2904 B at L=4, r=4.
 //
-// Mapping: one CTA = 32 consecutive queries of one batch item; one warp walks
-// 4 queries, its lanes fetch the L patches of a query with all loads in flight,
-// then produce the L*(2r+1)^2 samples.  Results are staged in a padded shared
-// tile [channel][query] so that the global store is channel-major and fully
-// coalesced (32 consecutive queries = one 128-byte line per channel); writing
-// them straight from the lanes would scatter 4-byte stores N*4 bytes apart.
+// Mapping: one CTA = QT (16 or 32) consecutive queries of one batch item.
+//   phase A  all 256 threads fetch the QT*L patches (QT*400 independent 4-byte
+//            loads at L=4, r=4, ~50 per thread, issued in unrolled batches so
+//            that thousands of loads are in flight per SM: the kernel is
+//            latency-bound, not bandwidth-bound, at feature-map sizes) into a
+//            shared [query][level][P][P] array with an odd row stride;
+//   phase B  thread <-> (query = lane, channel); the four weights of a level are
+//            computed once per level and thread; every channel is 4 LDS + 4 FMA
+//            and ONE coalesced store: the 32 lanes of a warp hold 32 consecutive
+//            queries of the same channel = one 128-byte line of the
+//            channel-major output.  No output staging, no bank conflicts (odd
+//            stride => lanes hit distinct banks).
 #include "common.cuh"
 
 namespace cf {
@@ -31,71 +37,143 @@ struct Pyramid {
     int W[CF_CORR_MAX_LEVELS];
 };
 
-constexpr int kQueriesPerCta = 32;
-constexpr int kLookupWarps = 8;
+constexpr int kLookupThreads = 256;
 
-// RADIUS > 0: compile-time radius; RADIUS == 0: use the runtime argument.
-template <int RADIUS>
-__global__ void __launch_bounds__(kLookupWarps * 32)
-corr_lookup_kernel(Pyramid pyr, const float *__restrict__ coords, float *__restrict__ out,
-                   int N, int levels, int radius_rt) {
+// RADIUS/LEVELS > 0: compile-time radius / level count (the models use 4 / 4);
+// 0: use the runtime arguments.
+template <int RADIUS, int LEVELS, int QT>
+__global__ void __launch_bounds__(kLookupThreads)
+corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict__ coords, float *__restrict__ out,
+                   int N, int levels_rt, int radius_rt) {
     extern __shared__ float smem[];
     const int r = RADIUS > 0 ? RADIUS : radius_rt;
+    const int levels = LEVELS > 0 ? LEVELS : levels_rt;
     const int K = 2 * r + 1, P = K + 1, KK = K * K, PP = P * P;
-    const int C = levels * KK;
-    constexpr int TS = kQueriesPerCta + 1;  // padded row: conflict-free column writes
-    float *tile = smem;                     // [C][TS]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *patch = smem + (size_t)C * TS + (size_t)warp * levels * PP;  // [levels][P][P]
-
+    const int LPP = levels * PP;
+    const int PS = LPP | 1;              // odd stride between queries
+    float *patch = smem;                 // [QT][PS]
+    float *cxy = smem + (size_t)QT * PS; // [QT][2]
+    const int tid = threadIdx.x;
     const int b = blockIdx.y;
-    const int q0 = blockIdx.x * kQueriesPerCta;
+    const int q0 = blockIdx.x * QT;
     const float *cb = coords + (size_t)b * 2 * N;
 
-    for (int qi = warp; qi < kQueriesPerCta; qi += kLookupWarps) {
-        const int q = q0 + qi;
-        if (q >= N) break;
+    if (tid < QT) {
+        const int q = q0 + tid;
         // clamp keeps (int) conversions defined for wild coordinates; anything
-        // this far out samples only zero padding anyway
-        const float cx = fminf(fmaxf(__ldg(cb + q), -1.0e6f), 1.0e6f);
-        const float cy = fminf(fmaxf(__ldg(cb + N + q), -1.0e6f), 1.0e6f);
-        const size_t map = (size_t)b * N + q;
+        // this far out samples only zero padding anyway (NaN clamps to the bound)
+        cxy[2 * tid] = q < N ? fminf(fmaxf(__ldg(cb + q), -1.0e6f), 1.0e6f) : 0.f;
+        cxy[2 * tid + 1] = q < N ? fminf(fmaxf(__ldg(cb + N + q), -1.0e6f), 1.0e6f) : 0.f;
+    }
+    __syncthreads();
 
-        for (int e = lane; e < levels * PP; e += 32) {
+    // ---- phase A: gather the patches (zero outside the map) ----------------------
+    if constexpr (RADIUS == 4 && LEVELS == 4) {
+        // warp <-> query, lane <-> patch element; per level the 100 elements are covered by 4
+        // rounds of 32 lanes, so level, row and column of a lane's element are loop constants
+        // and the 16 loads of a query are all in flight before the first shared-memory store.
+        constexpr int QPW = QT / (kLookupThreads / 32);
+        const int warp = tid >> 5, lane = tid & 31;
+        int py[4], px[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int e = lane + 32 * t;
+            py[t] = e / 10;
+            px[t] = e - py[t] * 10;
+        }
+#pragma unroll 1
+        for (int qq = 0; qq < QPW; ++qq) {
+            const int qi = warp * QPW + qq, q = q0 + qi;
+            const float cx = cxy[2 * qi], cy = cxy[2 * qi + 1];
+            float v[16];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const float inv = 1.f / (float)(1 << l);  // exact: coords / 2**l
+                const int X0 = (int)floorf(cx * inv) - 4, Y0 = (int)floorf(cy * inv) - 4;
+                const int Hl = pyr.H[l], Wl = pyr.W[l];
+                const float *base = pyr.ptr[l] + ((size_t)b * N + q) * Hl * Wl;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int X = X0 + px[t], Y = Y0 + py[t];
+                    const bool ok = q < N && (lane + 32 * t) < 100 && X >= 0 && X < Wl && Y >= 0 && Y < Hl;
+                    v[l * 4 + t] = ok ? __ldg(base + Y * Wl + X) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (lane + 32 * t < 100) patch[qi * PS + l * 100 + lane + 32 * t] = v[l * 4 + t];
+        }
+    } else {
+        const int total = QT * LPP;
+#pragma unroll 5
+        for (int idx = tid; idx < total; idx += kLookupThreads) {
+            const int qi = idx / LPP, e = idx - qi * LPP;
             const int l = e / PP, rem = e - l * PP;
             const int py = rem / P, px = rem - py * P;
             const float inv = 1.f / (float)(1 << l);  // exact: coords / 2**l
-            const int X = (int)floorf(cx * inv) - r + px;
-            const int Y = (int)floorf(cy * inv) - r + py;
+            const int X = (int)floorf(cxy[2 * qi] * inv) - r + px;
+            const int Y = (int)floorf(cxy[2 * qi + 1] * inv) - r + py;
             const int Hl = pyr.H[l], Wl = pyr.W[l];
+            const int q = q0 + qi;
             float v = 0.f;
-            if (X >= 0 && X < Wl && Y >= 0 && Y < Hl)
-                v = __ldg(pyr.ptr[l] + (map * Hl + Y) * Wl + X);
-            patch[e] = v;
+            if (q < N && X >= 0 && X < Wl && Y >= 0 && Y < Hl)
+                v = __ldg(pyr.ptr[l] + (((size_t)b * N + q) * Hl + Y) * Wl + X);
+            patch[qi * PS + e] = v;
         }
-        __syncwarp();
-        for (int o = lane; o < C; o += 32) {
-            const int l = o / KK, rem = o - l * KK;
-            const int i = rem / K, j = rem - i * K;  // i -> x offset, j -> y offset
+    }
+    __syncthreads();
+
+    // ---- phase B: bilinear samples, coalesced channel-major stores ---------------
+    constexpr int CPW = 32 / QT;                      // channels per warp-iteration
+    const int warp = tid >> 5, lane = tid & 31;
+    const int qi = lane % QT;
+    const int q = q0 + qi;
+    const int c_first = warp * CPW + lane / QT;
+    constexpr int c_step = (kLookupThreads / 32) * CPW;
+    const float cx = cxy[2 * qi], cy = cxy[2 * qi + 1];
+    const float *pq = patch + qi * PS;
+    float *ob = out + (size_t)b * levels * KK * N + q;
+    if (q < N) {
+        for (int l = 0; l < levels; ++l) {
             const float inv = 1.f / (float)(1 << l);
             const float sx = cx * inv, sy = cy * inv;
             const float fx = sx - floorf(sx), fy = sy - floorf(sy);
-            const float *pp = patch + l * PP + j * P + i;
-            const float v00 = pp[0], v01 = pp[1], v10 = pp[P], v11 = pp[P + 1];
-            float acc = v00 * ((1.f - fx) * (1.f - fy));
-            acc += v01 * (fx * (1.f - fy));
-            acc += v10 * ((1.f - fx) * fy);
-            acc += v11 * (fx * fy);
-            tile[o * TS + qi] = acc;
+            const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+            const float *pl = pq + l * PP;
+            float *ol = ob + (size_t)l * KK * N;
+#pragma unroll 4
+            for (int c = c_first; c < KK; c += c_step) {
+                const int i = c / K, j = c - i * K;   // i -> x offset, j -> y offset (transposed window)
+                const float *pp = pl + j * P + i;
+                float acc = pp[0] * w00;
+                acc += pp[1] * w01;
+                acc += pp[P] * w10;
+                acc += pp[P + 1] * w11;
+                ol[(size_t)c * N] = acc;
+            }
         }
-        __syncwarp();
     }
-    __syncthreads();
-    const int q = q0 + lane;
-    if (q < N) {
-        float *ob = out + (size_t)b * C * N + q;
-        for (int ch = warp; ch < C; ch += kLookupWarps) ob[(size_t)ch * N] = tile[ch * TS + lane];
+}
+
+template <int RADIUS, int LEVELS, int QT>
+static int launch_lookup(const Pyramid &pyr, const float *coords, float *out, int B, int N, int levels, int radius,
+                         cudaStream_t stream) {
+    const int K = 2 * radius + 1, P = K + 1;
+    const size_t smem = ((size_t)QT * ((levels * P * P) | 1) + 2 * QT) * sizeof(float);
+    CF_REQUIRE(smem <= 200 * 1024, CF_ERR_INVALID_ARG, "cf_corr_lookup: levels*radius too large for shared memory");
+    int dev = 0;
+    CF_CUDA(cudaGetDevice(&dev));
+    static bool opt_in[64] = {};
+    if (!opt_in[dev & 63]) {
+        CF_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RADIUS, LEVELS, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        opt_in[dev & 63] = true;
     }
+    dim3 grid((unsigned)ceil_div(N, QT), B);
+    corr_lookup_kernel<RADIUS, LEVELS, QT><<<grid, kLookupThreads, smem, stream>>>(pyr, coords, out, N, levels, radius);
+    CF_LAUNCH_CHECK("corr_lookup_kernel");
+    return CF_OK;
 }
 
 }  // namespace cf
@@ -119,22 +197,14 @@ extern "C" int cf_corr_lookup(const float *const *pyramid, const float *coords, 
         pyr.H[l] = h >> l;
         pyr.W[l] = w >> l;
     }
-    const int N = h * w, K = 2 * radius + 1, P = K + 1;
-    const int C = levels * K * K;
-    const size_t smem = ((size_t)C * (kQueriesPerCta + 1) + (size_t)kLookupWarps * levels * P * P) * sizeof(float);
-    CF_REQUIRE(smem <= 200 * 1024, CF_ERR_INVALID_ARG, "cf_corr_lookup: levels*radius too large for shared memory");
+    const int N = h * w;
     cudaStream_t stream = (cudaStream_t)stream_;
-    dim3 grid((unsigned)ceil_div(N, kQueriesPerCta), B);
-    int dev = 0;
-    CF_CUDA(cudaGetDevice(&dev));
-    static bool smem_opt_in[2][64] = {};
-    auto kern = radius == 4 ? corr_lookup_kernel<4> : corr_lookup_kernel<0>;
-    bool &done = smem_opt_in[radius == 4][dev & 63];
-    if (!done) {
-        CF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        done = true;
+    // 16 queries per CTA when the problem is small (more CTAs than SMs), else 32 (128-byte stores)
+    const bool small = (int64_t)B * ceil_div(N, 32) < 4 * (int64_t)sm_count();
+    if (radius == 4 && levels == 4) {
+        return small ? launch_lookup<4, 4, 16>(pyr, coords, out, B, N, levels, radius, stream)
+                     : launch_lookup<4, 4, 32>(pyr, coords, out, B, N, levels, radius, stream);
     }
-    kern<<<grid, kLookupWarps * 32, smem, stream>>>(pyr, coords, out, N, levels, radius);
-    CF_LAUNCH_CHECK("corr_lookup_kernel");
-    return CF_OK;
+    return small ? launch_lookup<0, 0, 16>(pyr, coords, out, B, N, levels, radius, stream)
+                 : launch_lookup<0, 0, 32>(pyr, coords, out, B, N, levels, radius, stream);
 }

@@ -186,7 +186,6 @@ rs_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t
 // exclusive scan of `n` counters in place, single CTA of 1024 threads
 __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ data, int64_t n) {
     __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t per = (n + 1023) / 1024;
     const int64_t s = (int64_t)tid * per, e = min(n, s + per);
@@ -208,7 +207,6 @@ __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ da
             if (lane >= o) ti += v;
         }
         warp_tot[lane] = ti - t;
-        if (lane == 31) carry_s = ti;
     }
     __syncthreads();
     uint32_t run = warp_tot[warp] + inc - sum;
@@ -217,7 +215,6 @@ __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ da
         data[i] = run;
         run += v;
     }
-    (void)carry_s;
 }
 
 // Stable scatter of one 8-bit digit.  Order inside a CTA tile: warp-major,
@@ -360,13 +357,22 @@ voxel_stats_kernel(const float *__restrict__ grid, int64_t cells, int64_t chunk_
     double sum = 0.0, sumsq = 0.0;
     long long nnz = 0;
     float mn = INFINITY, mx = -INFINITY;
-    for (int64_t i = s + threadIdx.x; i < e; i += kStatThreads) {
-        const float v = hot_filter(__ldg(g + i), hot_thr);
+    auto take = [&](float raw) {
+        const float v = hot_filter(raw, hot_thr);
         sum += (double)v;
         sumsq += (double)v * (double)v;
         nnz += (v != 0.f);
         mn = fminf(mn, v);
         mx = fmaxf(mx, v);
+    };
+    if (((cells | chunk_len) & 3) == 0) {  // 128-bit loads (chunk starts stay 16-byte aligned)
+        const float4 *g4 = reinterpret_cast<const float4 *>(g);
+        for (int64_t i = (s >> 2) + threadIdx.x; i < (e >> 2); i += kStatThreads) {
+            const float4 q = __ldg(g4 + i);
+            take(q.x); take(q.y); take(q.z); take(q.w);
+        }
+    } else {
+        for (int64_t i = s + threadIdx.x; i < e; i += kStatThreads) take(__ldg(g + i));
     }
     // fixed-shape tree: deterministic for a given launch geometry
     sum = warp_sum(sum); sumsq = warp_sum(sumsq); nnz = warp_sum(nnz);
@@ -386,10 +392,10 @@ voxel_stats_kernel(const float *__restrict__ grid, int64_t cells, int64_t chunk_
 }
 
 __global__ void __launch_bounds__(kStatThreads)
-voxel_normalise_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t cells, int64_t chunk_len,
+voxel_normalise_kernel(const float *in, float *out /* may alias in */, int64_t cells, int64_t chunk_len,
                        float hot_thr, int mode, const Partial *__restrict__ partials, int chunks) {
     const int b = blockIdx.y, c = blockIdx.x;
-    __shared__ double s_a, s_b;   // out = (v - s_a) * (1/s_b) semantics below
+    __shared__ double s_a, s_b;   // out = (v - s_a) * s_b
     __shared__ int s_identity;
     if (threadIdx.x < 32) {
         // every CTA of a window re-reduces the window's partials in the same fixed order
@@ -409,27 +415,37 @@ voxel_normalise_kernel(const float *__restrict__ in, float *__restrict__ out, in
                 const double mean = nnz ? sum / (double)nnz : 0.0;
                 const double var = nnz ? sumsq / (double)nnz - mean * mean : 0.0;
                 s_a = mean;
-                s_b = sqrt(fmax(var, 0.0)) + 1e-8;
+                s_b = 1.0 / (sqrt(fmax(var, 0.0)) + 1e-8);
             } else {
                 s_identity = 0;
                 s_a = (double)mn;
-                s_b = (double)mx - (double)mn + 1e-8;
+                s_b = 1.0 / ((double)mx - (double)mn + 1e-8);
             }
         }
     }
     __syncthreads();
-    const double a = s_a, d = s_b;
+    const double a = s_a, inv = s_b;
     const bool identity = s_identity != 0;
     const float *g = in + (int64_t)b * cells;
     float *o = out + (int64_t)b * cells;
     const int64_t s = (int64_t)c * chunk_len, e = min(cells, s + chunk_len);
-    for (int64_t i = s + threadIdx.x; i < e; i += kStatThreads) {
-        const float v = hot_filter(__ldg(g + i), hot_thr);
-        float r;
-        if (identity) r = v;
-        else if (mode == CF_PRE_STD) r = (v != 0.f) ? (float)(((double)v - a) / d) : 0.f;
-        else r = (float)(((double)v - a) / d);
-        o[i] = r;
+    // one fp64 subtract + multiply per NON-ZERO cell (a true fp64 divide per cell made this
+    // kernel 3x slower than the scatter itself); the result is rounded once to fp32
+    auto norm = [&](float raw) -> float {
+        const float v = hot_filter(raw, hot_thr);
+        if (identity) return v;
+        if (mode == CF_PRE_STD) return (v != 0.f) ? (float)(((double)v - a) * inv) : 0.f;
+        return (float)(((double)v - a) * inv);
+    };
+    if (((cells | chunk_len) & 3) == 0) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(g);
+        float4 *o4 = reinterpret_cast<float4 *>(o);
+        for (int64_t i = (s >> 2) + threadIdx.x; i < (e >> 2); i += kStatThreads) {
+            const float4 q = g4[i];
+            o4[i] = make_float4(norm(q.x), norm(q.y), norm(q.z), norm(q.w));
+        }
+    } else {
+        for (int64_t i = s + threadIdx.x; i < e; i += kStatThreads) o[i] = norm(g[i]);
     }
 }
 
@@ -441,6 +457,7 @@ static void stat_geometry(int B, int64_t cells, int &chunks, int64_t &chunk_len)
     if (chunks > cap) chunks = (int)(cap < 1 ? 1 : cap);
     if (chunks > kMaxChunks) chunks = kMaxChunks;
     chunk_len = ceil_div(cells, chunks);
+    chunk_len = (chunk_len + 3) & ~(int64_t)3;  // keeps every chunk start 16-byte aligned
 }
 
 static int run_preprocess(const float *in, float *out, int B, int64_t cells, int preprocess, float hot_thr,

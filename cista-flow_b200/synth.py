@@ -56,11 +56,34 @@ def soft_shrink(x: np.ndarray, lam: float) -> np.ndarray:
     return np.sign(x) * np.maximum(np.abs(x) - lam, 0.0)
 
 
+def smooth_field(rng, batch: int, channels: int, height: int, width: int, sigma: float, cell: int = 16) -> np.ndarray:
+    """Low-frequency random field: N(0, sigma^2) on a coarse grid (one node per
+    ``cell`` pixels), bilinearly interpolated -- neighbouring pixels move together,
+    like real optical flow."""
+    ch, cw = max(2, height // cell + 1), max(2, width // cell + 1)
+    coarse = sigma * rng.standard_normal((batch, channels, ch, cw))
+    ys = np.linspace(0, ch - 1, height)
+    xs = np.linspace(0, cw - 1, width)
+    y0 = np.minimum(ys.astype(np.int64), ch - 2)
+    x0 = np.minimum(xs.astype(np.int64), cw - 2)
+    fy = (ys - y0)[:, None]
+    fx = (xs - x0)[None, :]
+    c00 = coarse[:, :, y0][:, :, :, x0]
+    c01 = coarse[:, :, y0][:, :, :, x0 + 1]
+    c10 = coarse[:, :, y0 + 1][:, :, :, x0]
+    c11 = coarse[:, :, y0 + 1][:, :, :, x0 + 1]
+    return ((1 - fy) * ((1 - fx) * c00 + fx * c01) + fy * ((1 - fx) * c10 + fx * c11)).astype(np.float32)
+
+
 def warp_inputs(batch: int, height: int, width: int, seed: int, code_channels: int = 128,
-                flow_sigma: float = 5.0):
+                flow_sigma: float = 5.0, flow_kind: str = "noise"):
     """(img, codes, flow): img ~ U(0,1); codes ~ soft-shrunk N(0,1) (about 60 %
-    zeros, like real sparse codes); flow ~ N(0, sigma^2) px plus a smooth
-    affine component."""
+    zeros, like real sparse codes).  flow_kind:
+      'noise'   independent N(0, sigma^2) px per pixel + an affine component: the
+                adversarial case for the gather (every tap of a warp in a
+                different cache line) -- used by the parity tests;
+      'smooth'  low-frequency field of the same magnitude + affine component +
+                0.05 px jitter: what a flow network produces -- used by bench.py."""
     rng = np.random.default_rng(seed)
     img = rng.random((batch, 1, height, width), dtype=np.float32)
     codes = soft_shrink(rng.standard_normal((batch, code_channels, height // 2, width // 2),
@@ -68,9 +91,12 @@ def warp_inputs(batch: int, height: int, width: int, seed: int, code_channels: i
     yy, xx = np.meshgrid(np.linspace(-1, 1, height, dtype=np.float32),
                          np.linspace(-1, 1, width, dtype=np.float32), indexing="ij")
     smooth = np.stack([3.0 * xx - 2.0 * yy, 1.5 * yy + 2.5 * xx])[None]
-    flow = (flow_sigma * rng.standard_normal((batch, 2, height, width), dtype=np.float32)
-            + smooth).astype(np.float32)
-    return img, codes, flow
+    if flow_kind == "smooth":
+        flow = smooth_field(rng, batch, 2, height, width, flow_sigma) + smooth \
+            + 0.05 * rng.standard_normal((batch, 2, height, width), dtype=np.float32)
+    else:
+        flow = flow_sigma * rng.standard_normal((batch, 2, height, width), dtype=np.float32) + smooth
+    return img, codes, flow.astype(np.float32)
 
 
 def padded_dims(height: int, width: int, multiple: int = 32):
