@@ -65,7 +65,7 @@ corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict_
         cxy[2 * tid] = q < N ? fminf(fmaxf(__ldg(cb + q), -1.0e6f), 1.0e6f) : 0.f;
         cxy[2 * tid + 1] = q < N ? fminf(fmaxf(__ldg(cb + N + q), -1.0e6f), 1.0e6f) : 0.f;
     }
-    __syncthreads();
+    if constexpr (!(RADIUS == 4 && LEVELS == 4)) __syncthreads();  // the generic gather reads cxy[]
 
     // ---- phase A: gather the patches (zero outside the map) ----------------------
     if constexpr (RADIUS == 4 && LEVELS == 4) {
@@ -81,29 +81,41 @@ corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict_
             py[t] = e / 10;
             px[t] = e - py[t] * 10;
         }
+        // two queries per pass: 32 independent loads per lane are in flight before the first store
+        constexpr int U = 2;
+        static_assert(QPW % U == 0, "queries per warp must be even");
 #pragma unroll 1
-        for (int qq = 0; qq < QPW; ++qq) {
-            const int qi = warp * QPW + qq, q = q0 + qi;
-            const float cx = cxy[2 * qi], cy = cxy[2 * qi + 1];
-            float v[16];
+        for (int qq = 0; qq < QPW; qq += U) {
+            float v[U][16];
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                const float inv = 1.f / (float)(1 << l);  // exact: coords / 2**l
-                const int X0 = (int)floorf(cx * inv) - 4, Y0 = (int)floorf(cy * inv) - 4;
-                const int Hl = pyr.H[l], Wl = pyr.W[l];
-                const float *base = pyr.ptr[l] + ((size_t)b * N + q) * Hl * Wl;
+            for (int u = 0; u < U; ++u) {
+                const int qi = warp * QPW + qq + u, q = q0 + qi;
+                // lane-uniform loads straight from global: phase A does not wait for the cxy[] staging
+                const float cx = q < N ? fminf(fmaxf(__ldg(cb + q), -1.0e6f), 1.0e6f) : 0.f;
+                const float cy = q < N ? fminf(fmaxf(__ldg(cb + N + q), -1.0e6f), 1.0e6f) : 0.f;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int X = X0 + px[t], Y = Y0 + py[t];
-                    const bool ok = q < N && (lane + 32 * t) < 100 && X >= 0 && X < Wl && Y >= 0 && Y < Hl;
-                    v[l * 4 + t] = ok ? __ldg(base + Y * Wl + X) : 0.f;
+                for (int l = 0; l < 4; ++l) {
+                    const float inv = 1.f / (float)(1 << l);  // exact: coords / 2**l
+                    const int X0 = (int)floorf(cx * inv) - 4, Y0 = (int)floorf(cy * inv) - 4;
+                    const int Hl = pyr.H[l], Wl = pyr.W[l];
+                    const float *base = pyr.ptr[l] + ((size_t)b * N + q) * Hl * Wl;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int X = X0 + px[t], Y = Y0 + py[t];
+                        const bool ok = q < N && (lane + 32 * t) < 100 && X >= 0 && X < Wl && Y >= 0 && Y < Hl;
+                        v[u][l * 4 + t] = ok ? __ldg(base + Y * Wl + X) : 0.f;
+                    }
                 }
             }
 #pragma unroll
-            for (int l = 0; l < 4; ++l)
+            for (int u = 0; u < U; ++u) {
+                const int qi = warp * QPW + qq + u;
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (lane + 32 * t < 100) patch[qi * PS + l * 100 + lane + 32 * t] = v[l * 4 + t];
+                for (int l = 0; l < 4; ++l)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (lane + 32 * t < 100) patch[qi * PS + l * 100 + lane + 32 * t] = v[u][l * 4 + t];
+            }
         }
     } else {
         const int total = QT * LPP;

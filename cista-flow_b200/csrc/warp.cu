@@ -9,10 +9,12 @@
 // Data layout in HBM: img/out [B,C,H,W], flow [B,2,fH,fW], all fp32 row-major.
 // Roofline: HBM.  Algorithmic bytes per call = B*H*W*(8*C + 8): every input
 // and output channel once plus the two flow channels.  The gather has high
-// spatial locality, so the 4 taps of neighbouring threads coalesce into the
-// same 128-byte lines and hit L1/L2; one thread owns one output pixel, computes
-// the sample position once and streams CPT channels with all 4*CPT loads in
-// flight before the first FMA (memory-level parallelism instead of occupancy).
+// spatial locality (network flow is smooth: it is predicted at 1/8 resolution
+// and up-sampled), so the 4 taps of neighbouring threads fall into the same
+// 128-byte lines.  One CTA owns a 32x8 pixel tile (the two tap rows of a pixel
+// row are re-used by the row below out of L1), one thread owns one output
+// pixel, computes the sample position once and streams its channel group in
+// batches of CPT channels with all 4*CPT loads in flight before the first FMA.
 // No fast-math in this file: the position arithmetic mirrors ATen's operation
 // order (true fp32 division) so that floor() picks the same taps.
 #include "common.cuh"
@@ -118,34 +120,39 @@ struct WarpJob {
     int C, H, W;          // geometry of img/out
     int half;             // 1: flow is [2, fH, fW] at twice the resolution
     float sy, sx;         // align_corners scales for the fused down-sampling
-    int blocks_x;         // pixel tiles per (batch, channel group)
+    int tiles_x;          // 32-pixel-wide tiles per row
+    int blocks_x;         // pixel tiles (32x8) per (batch, channel group)
+    int cpg;              // channels per group (one thread loops over them, CPT at a time)
     int groups;           // channel groups
 };
+constexpr int kTileW = 32, kTileH = 8;
 
 template <int CPT>
 __device__ __forceinline__ void run_job(const WarpJob &j, const float *__restrict__ flow,
                                         int fH, int fW, float sign, int tile, int group, int b) {
-    const int plane_i = j.H * j.W;
-    const int p = tile * blockDim.x + threadIdx.x;
-    if (p >= plane_i) return;
-    const int y = p / j.W, x = p - y * j.W;
+    const int ty = tile / j.tiles_x, tx = tile - ty * j.tiles_x;
+    const int x = tx * kTileW + (threadIdx.x & 31), y = ty * kTileH + (threadIdx.x >> 5);
+    if (x >= j.W || y >= j.H) return;
+    const int p = y * j.W + x;
     const float *fb = flow + (size_t)b * 2 * fH * fW;
     const float2 uv = flow_at(fb, x, y, j.W, fH, fW, j.half != 0, j.sy, j.sx);
     const Taps t = make_taps(uv.x, uv.y, x, y, j.H, j.W, sign);
-    const size_t plane = (size_t)plane_i;
-    warp_pixel<CPT>(j.img + (size_t)b * j.C * plane, j.out + (size_t)b * j.C * plane, t, p,
-                    group * CPT, j.C, plane);
+    const size_t plane = (size_t)j.H * j.W;
+    const float *img_b = j.img + (size_t)b * j.C * plane;
+    float *out_b = j.out + (size_t)b * j.C * plane;
+    const int c_end = min(j.C, (group + 1) * j.cpg);
+    for (int c0 = group * j.cpg; c0 < c_end; c0 += CPT) warp_pixel<CPT>(img_b, out_b, t, p, c0, c_end, plane);
 }
 
 template <int CPT>
-__global__ void __launch_bounds__(256) warp_gather_kernel(WarpJob j, const float *__restrict__ flow,
+__global__ void __launch_bounds__(256, 4) warp_gather_kernel(WarpJob j, const float *__restrict__ flow,
                                                           int fH, int fW, float sign) {
     run_job<CPT>(j, flow, fH, fW, sign, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
-// image (CPT=1 per thread, few channels) + codes (CPT=16) in one launch:
+// image (CPT=1 per thread, few channels) + codes (CPT=8, 32 channels per thread) in one launch:
 // blockIdx.x < img.blocks_x*img.groups -> image part, the rest -> codes part.
-__global__ void __launch_bounds__(256) warp_frame_and_codes_kernel(WarpJob ji, WarpJob jz,
+__global__ void __launch_bounds__(256, 4) warp_frame_and_codes_kernel(WarpJob ji, WarpJob jz,
                                                                    const float *__restrict__ flow,
                                                                    int fH, int fW, float sign) {
     const int b = blockIdx.y;
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(256) warp_frame_and_codes_kernel(WarpJob ji, W
         run_job<1>(ji, flow, fH, fW, sign, blk % ji.blocks_x, blk / ji.blocks_x, b);
     } else {
         blk -= n_img;
-        run_job<16>(jz, flow, fH, fW, sign, blk % jz.blocks_x, blk / jz.blocks_x, b);
+        run_job<8>(jz, flow, fH, fW, sign, blk % jz.blocks_x, blk / jz.blocks_x, b);
     }
 }
 
@@ -171,8 +178,10 @@ static int make_job(WarpJob &j, const float *img, float *out, int C, int H, int 
         set_error("cf_warp: flow is %dx%d but the image is %dx%d (must be equal, or image == flow/2)", fH, fW, H, W);
         return CF_ERR_INVALID_ARG;
     }
-    j.blocks_x = (int)ceil_div((int64_t)H * W, 256);
-    j.groups = (int)ceil_div(C, cpt);
+    j.tiles_x = (int)ceil_div(W, kTileW);
+    j.blocks_x = j.tiles_x * (int)ceil_div(H, kTileH);
+    j.cpg = C >= 4 * cpt ? 4 * cpt : (int)ceil_div(C, cpt) * cpt;  // up to 4 batches of CPT channels per thread
+    j.groups = (int)ceil_div(C, j.cpg);
     return CF_OK;
 }
 
@@ -190,12 +199,12 @@ extern "C" int cf_warp(const float *img, const float *flow, float *out, int B, i
     CF_REQUIRE(B <= 65535, CF_ERR_INVALID_ARG, "cf_warp: B > 65535");
     if (B == 0 || C == 0) return CF_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int cpt = C >= 16 ? 16 : (C >= 4 ? 4 : 1);
+    const int cpt = C >= 8 ? 8 : (C >= 4 ? 4 : 1);
     WarpJob j;
     if (int rc = make_job(j, img, out, C, H, W, flowH, flowW, cpt)) return rc;
     CF_REQUIRE(j.groups <= 65535, CF_ERR_INVALID_ARG, "cf_warp: too many channels");
     dim3 grid(j.blocks_x, j.groups, B);
-    if (cpt == 16) warp_gather_kernel<16><<<grid, 256, 0, stream>>>(j, flow, flowH, flowW, sign);
+    if (cpt == 8) warp_gather_kernel<8><<<grid, 256, 0, stream>>>(j, flow, flowH, flowW, sign);
     else if (cpt == 4) warp_gather_kernel<4><<<grid, 256, 0, stream>>>(j, flow, flowH, flowW, sign);
     else warp_gather_kernel<1><<<grid, 256, 0, stream>>>(j, flow, flowH, flowW, sign);
     CF_LAUNCH_CHECK("warp_gather_kernel");
@@ -216,7 +225,7 @@ extern "C" int cf_warp_frame_and_codes(const float *img, const float *codes, con
     cudaStream_t stream = (cudaStream_t)stream_;
     WarpJob ji, jz;
     if (int rc = make_job(ji, img, img_out, Ci, H, W, H, W, 1)) return rc;
-    if (int rc = make_job(jz, codes, codes_out, Cz, H / 2, W / 2, H, W, 16)) return rc;
+    if (int rc = make_job(jz, codes, codes_out, Cz, H / 2, W / 2, H, W, 8)) return rc;
     dim3 grid(ji.blocks_x * ji.groups + jz.blocks_x * jz.groups, B);
     warp_frame_and_codes_kernel<<<grid, 256, 0, stream>>>(ji, jz, flow, H, W, sign);
     CF_LAUNCH_CHECK("warp_frame_and_codes_kernel");

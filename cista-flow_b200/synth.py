@@ -82,8 +82,12 @@ def warp_inputs(batch: int, height: int, width: int, seed: int, code_channels: i
       'noise'   independent N(0, sigma^2) px per pixel + an affine component: the
                 adversarial case for the gather (every tap of a warp in a
                 different cache line) -- used by the parity tests;
-      'smooth'  low-frequency field of the same magnitude + affine component +
-                0.05 px jitter: what a flow network produces -- used by bench.py."""
+      'smooth'  what a flow network produces: the nets predict flow at 1/8
+                resolution and up-sample it, so neighbouring pixels move together.
+                Calibrated on the flow_final tensors recorded from the reference
+                models (tests/golden/trace_*.npz: std 1.4-2.1 px, max ~9 px, mean
+                |d flow/dx| 0.06 px/px): N(0, 2^2) px nodes every 32 px, bilinearly
+                interpolated, + the affine component + 0.02 px jitter -- used by bench.py."""
     rng = np.random.default_rng(seed)
     img = rng.random((batch, 1, height, width), dtype=np.float32)
     codes = soft_shrink(rng.standard_normal((batch, code_channels, height // 2, width // 2),
@@ -92,8 +96,8 @@ def warp_inputs(batch: int, height: int, width: int, seed: int, code_channels: i
                          np.linspace(-1, 1, width, dtype=np.float32), indexing="ij")
     smooth = np.stack([3.0 * xx - 2.0 * yy, 1.5 * yy + 2.5 * xx])[None]
     if flow_kind == "smooth":
-        flow = smooth_field(rng, batch, 2, height, width, flow_sigma) + smooth \
-            + 0.05 * rng.standard_normal((batch, 2, height, width), dtype=np.float32)
+        flow = smooth_field(rng, batch, 2, height, width, 0.4 * flow_sigma, cell=32) + smooth \
+            + 0.02 * rng.standard_normal((batch, 2, height, width), dtype=np.float32)
     else:
         flow = flow_sigma * rng.standard_normal((batch, 2, height, width), dtype=np.float32) + smooth
     return img, codes, flow.astype(np.float32)

@@ -199,3 +199,36 @@ def test_sharding_world_size_2_gloo(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "OK 0" in res.stdout and "OK 1" in res.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/e2v"), reason="reference checkout only exists in the build container")
+def test_install_against_the_real_reference_modules():
+    """install() rebinds the names inside the reference's own modules (CPU: import + rebind only)."""
+    code = r"""
+import sys, types
+sys.dont_write_bytecode = True
+sys.path.insert(0, "/root/reference"); sys.path.insert(0, %r)
+mpl = types.ModuleType("matplotlib"); plt = types.ModuleType("matplotlib.pyplot"); mpl.pyplot = plt
+sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = plt
+oc = types.ModuleType("omegaconf")
+class OmegaConf:
+    create = staticmethod(lambda d: types.SimpleNamespace(**d))
+oc.OmegaConf = OmegaConf; sys.modules["omegaconf"] = oc
+import e2v.e2v_model, ERAFT.eraft, DCEIFlow.DCEIFlow, data_readers.video_readers
+import cistaflow_b200 as cf
+done = cf.install()
+assert e2v.e2v_model.FrameWarp is cf.FrameWarp
+assert ERAFT.eraft.CorrBlock is cf.CorrBlock and DCEIFlow.DCEIFlow.CorrBlock is cf.CorrBlock
+assert data_readers.video_readers.events_to_voxel_grid is cf.events_to_voxel_grid
+assert data_readers.video_readers.event_preprocess is cf.event_preprocess
+import argparse
+from utils.configs import set_configs
+p = argparse.ArgumentParser(); set_configs(p)
+m = e2v.e2v_model.ERAFTCistaNet(p.parse_args(["--model_mode", "cista-eraft", "--base_channels", "8"]))
+assert isinstance(m.frame_warp, cf.FrameWarp)       # the model now owns OUR FrameWarp
+cf.uninstall()
+assert e2v.e2v_model.FrameWarp is not cf.FrameWarp
+print("OK", len(done))
+""" % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
