@@ -279,18 +279,6 @@ def run_ours(args, cfg):
         clocks = sampler.stop() if sampler else None
 
         # -- per-kernel timing (each kernel alone, rotating sets, CUDA events on this stream)
-        def time_op(fn, reps=20):
-            for i in range(3):
-                fn(dev_sets[i % N_SETS])
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for i in range(reps):
-                fn(dev_sets[i % N_SETS])
-            b.record(stream)
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps * 1e-3
-
         blocks = [cf.CorrBlock(d["fmap1"], d["fmap2"], num_levels=cfg["levels"], radius=cfg["radius"]) for d in dev_sets]
         lookup_out = [torch.empty_like(keep[0][1][0]) for _ in range(N_SETS)]
         vox_out = [torch.empty_like(keep[0][0]) for _ in range(N_SETS)]
@@ -392,8 +380,8 @@ def run_ours(args, cfg):
         "e2e": {"value": frames / (e2e_step_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_step_ms, "steps": e2e_steps,
                 "mevents_per_s": frames * cfg["events"] / (e2e_step_ms * 1e-3) / 1e6,
-                "path": "pinned host tensors -> H2D -> cistaflow_b200 public API -> D2H of voxel grids, 12 lookup "
-                        "outputs, warped frame + codes"},
+                "path": "pinned host tensors -> H2D -> cistaflow_b200 public API -> D2H of voxel "
+                        "grids, 12 lookup outputs, warped frame + codes"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roof,

@@ -148,22 +148,55 @@ corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict_
     const float *pq = patch + qi * PS;
     float *ob = out + (size_t)b * levels * KK * N + q;
     if (q < N) {
-        for (int l = 0; l < levels; ++l) {
-            const float inv = 1.f / (float)(1 << l);
-            const float sx = cx * inv, sy = cy * inv;
-            const float fx = sx - floorf(sx), fy = sy - floorf(sy);
-            const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
-            const float *pl = pq + l * PP;
-            float *ol = ob + (size_t)l * KK * N;
+        if constexpr (RADIUS == 4 && LEVELS == 4) {
+            // the (<= 11) channels of this thread are the same in every level: resolve their window
+            // position once, then each sample is 4 LDS + 4 FMA + 1 STG of straight-line code
+            constexpr int NCH = (81 + c_step - 1) / c_step;
+            int offs[NCH];
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int c = c_first + k * c_step;
+                const int i = c / 9, j = c - i * 9;  // i -> x offset, j -> y offset (transposed window)
+                offs[k] = j * 10 + i;
+            }
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const float inv = 1.f / (float)(1 << l);
+                const float sx = cx * inv, sy = cy * inv;
+                const float fx = sx - floorf(sx), fy = sy - floorf(sy);
+                const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+                const float *pl = pq + l * 100;
+                float *ol = ob + (size_t)(l * 81 + c_first) * N;
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    if (c_first + k * c_step < 81) {
+                        const float *pp = pl + offs[k];
+                        float acc = pp[0] * w00;
+                        acc += pp[1] * w01;
+                        acc += pp[10] * w10;
+                        acc += pp[11] * w11;
+                        ol[(size_t)(k * c_step) * N] = acc;
+                    }
+                }
+            }
+        } else {
+            for (int l = 0; l < levels; ++l) {
+                const float inv = 1.f / (float)(1 << l);
+                const float sx = cx * inv, sy = cy * inv;
+                const float fx = sx - floorf(sx), fy = sy - floorf(sy);
+                const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+                const float *pl = pq + l * PP;
+                float *ol = ob + (size_t)l * KK * N;
 #pragma unroll 4
-            for (int c = c_first; c < KK; c += c_step) {
-                const int i = c / K, j = c - i * K;   // i -> x offset, j -> y offset (transposed window)
-                const float *pp = pl + j * P + i;
-                float acc = pp[0] * w00;
-                acc += pp[1] * w01;
-                acc += pp[P] * w10;
-                acc += pp[P + 1] * w11;
-                ol[(size_t)c * N] = acc;
+                for (int c = c_first; c < KK; c += c_step) {
+                    const int i = c / K, j = c - i * K;   // i -> x offset, j -> y offset (transposed window)
+                    const float *pp = pl + j * P + i;
+                    float acc = pp[0] * w00;
+                    acc += pp[1] * w01;
+                    acc += pp[P] * w10;
+                    acc += pp[P + 1] * w11;
+                    ol[(size_t)c * N] = acc;
+                }
             }
         }
     }

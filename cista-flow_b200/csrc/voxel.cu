@@ -9,10 +9,19 @@
 // Roofline: HBM.  Algorithmic bytes per window = 32*N_events + 4*nb*H*W.
 //
 // Two accumulation modes:
-//   ATOMIC         scatter with fp32 RED.ADD resolved in L2 (the grid of a
-//                  window is written once, stays L2-resident while its events
-//                  stream in, and is normalised in place); sum order is
-//                  unspecified -> agrees with the reference to <= 1e-5.
+//   ATOMIC         sum order unspecified -> agrees with the reference to <= 1e-5.
+//                  fp32 RED.ADD resolved in L2; the batch is processed in chunks
+//                  of windows whose grids + events fit in L2 (<= 48 MB), each chunk
+//                  running zero -> scatter -> statistics -> normalise-in-place
+//                  back to back, so a grid is read and written in L2 and reaches
+//                  HBM exactly once.
+//                  Measured dead end, kept behind CF_VOXEL_FLAGS=2 for the record:
+//                  privatising the grid in the distributed shared memory of a
+//                  thread-block cluster and scattering with
+//                  red.shared::cluster.add.f32 (voxel_cluster_kernel).  DSMEM
+//                  atomics sustain ~19 G adds/s chip-wide vs ~69 G/s for L2
+//                  atomics on a B200, so that path is 2-4x SLOWER than the L2 one
+//                  (scripts/voxel_microbench.py).
 //   DETERMINISTIC  bit-exact.  The reference accumulates every cell
 //                  sequentially in event order, all bin-ti ("left")
 //                  contributions before all bin-ti+1 ("right") ones (two
@@ -23,7 +32,12 @@
 //                  adds (__fadd_rn / fp64 add + round for the NumPy flavour).
 // Time normalisation is fp64 with the reference's operation order
 // (mul, then div) in both modes, so bin assignment is identical.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace cf {
 
@@ -108,39 +122,213 @@ constexpr int kScatterThreads = 256;
 constexpr int kScatterUnroll = 4;
 
 __global__ void __launch_bounds__(kScatterThreads)
-voxel_scatter_atomic_kernel(const double *__restrict__ ev, const int64_t *__restrict__ off, int64_t total,
-                            int B, int nb, int H, int W, int flavour, float *__restrict__ out) {
-    const int64_t tile = (int64_t)blockIdx.x * (kScatterThreads * kScatterUnroll);
+voxel_scatter_atomic_kernel(const double *__restrict__ ev, const int64_t *__restrict__ off,
+                            int B, int nb, int H, int W, int flavour, float *__restrict__ out, int b_first, int b_end) {
+    // the events of windows [b_first, b_end) (one L2-sized chunk of the batch), grid-stride over
+    // tiles of 1024 events: the host does not know the chunk's event count (offsets are on the device)
+    const int64_t ev_first = __ldg(off + b_first), ev_end = __ldg(off + b_end);
     const int64_t plane = (int64_t)H * W;
     const int planes_per_bin = flavour == CF_FLAVOUR_POL ? 2 : 1;
+    constexpr int64_t kTileEvents = kScatterThreads * kScatterUnroll;
     Window w;
     w.b = -1;
-    Event e[kScatterUnroll];
+    for (int64_t tile = ev_first + (int64_t)blockIdx.x * kTileEvents; tile < ev_end; tile += (int64_t)gridDim.x * kTileEvents) {
+        Event e[kScatterUnroll];
 #pragma unroll
-    for (int k = 0; k < kScatterUnroll; ++k) {  // all loads in flight first
-        const int64_t i = tile + k * kScatterThreads + threadIdx.x;
-        if (i < total) e[k] = load_event(ev, i);
-    }
-#pragma unroll
-    for (int k = 0; k < kScatterUnroll; ++k) {
-        const int64_t i = tile + k * kScatterThreads + threadIdx.x;
-        if (i >= total) break;
-        locate_window(w, i, off, ev, B);
-        const Binned b = bin_event(e[k], w, nb, H, W, flavour);
-        if (!b.ok) continue;
-        float wl, wr;
-        if (flavour == CF_FLAVOUR_TORCH) {
-            weights_f32(b, wl, wr);
-        } else {
-            double dl, dr;
-            weights_f64(b, dl, dr);
-            wl = (float)dl;
-            wr = (float)dr;
+        for (int k = 0; k < kScatterUnroll; ++k) {  // all loads in flight first
+            const int64_t i = tile + k * kScatterThreads + threadIdx.x;
+            if (i < ev_end) e[k] = load_event(ev, i);
         }
-        float *cell = out + (((int64_t)w.b * nb + b.bin) * planes_per_bin + b.chan) * plane + (int64_t)b.y * W + b.x;
-        atomicAdd(cell, wl);  // result unused -> RED.E.ADD.F32
-        if (b.bin + 1 < nb) atomicAdd(cell + planes_per_bin * plane, wr);
+#pragma unroll
+        for (int k = 0; k < kScatterUnroll; ++k) {
+            const int64_t i = tile + k * kScatterThreads + threadIdx.x;
+            if (i >= ev_end) break;
+            locate_window(w, i, off, ev, B);
+            const Binned b = bin_event(e[k], w, nb, H, W, flavour);
+            if (!b.ok) continue;
+            float wl, wr;
+            if (flavour == CF_FLAVOUR_TORCH) {
+                weights_f32(b, wl, wr);
+            } else {
+                double dl, dr;
+                weights_f64(b, dl, dr);
+                wl = (float)dl;
+                wr = (float)dr;
+            }
+            float *cell = out + (((int64_t)w.b * nb + b.bin) * planes_per_bin + b.chan) * plane + (int64_t)b.y * W + b.x;
+            atomicAdd(cell, wl);  // result unused -> REDG.E.ADD.F32
+            if (b.bin + 1 < nb) atomicAdd(cell + planes_per_bin * plane, wr);
+        }
     }
+}
+
+// ----------------------------------------- atomic mode, cluster (smem) path ---
+struct alignas(16) Partial {
+    double sum, sumsq;
+    long long nnz;
+    float mn, mx;
+};
+
+__device__ __forceinline__ float hot_filter(float v, float thr) { return (thr > 0.f && fabsf(v) > thr) ? 0.f : v; }
+
+// fp32 add into the shared memory of CTA `rank` of this cluster (DSMEM), no return value
+__device__ __forceinline__ void red_add_cluster(float *local_ptr, unsigned rank, float v) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(local_ptr);
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    asm volatile("red.relaxed.cluster.shared::cluster.add.f32 [%0], %1;" ::"r"(r), "f"(v) : "memory");
+}
+
+constexpr int kClusterThreads = 256;
+
+__global__ void __launch_bounds__(kClusterThreads)
+voxel_cluster_kernel(const double *__restrict__ ev, const int64_t *__restrict__ off, int B, int nb, int H, int W,
+                     int flavour, int preprocess, float hot_thr, float *__restrict__ out, int slice) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank(), CS = cluster.num_blocks();
+    extern __shared__ __align__(16) float sm[];          // [slice] grid slice, then one Partial
+    Partial *part = reinterpret_cast<Partial *>(sm + slice);
+    __shared__ Partial warp_part[kClusterThreads / 32];
+    __shared__ double s_a, s_inv;
+    __shared__ int s_identity;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int planes = flavour == CF_FLAVOUR_POL ? 2 : 1;
+    const int64_t plane = (int64_t)H * W;
+    const int cells = (int)((int64_t)nb * planes * plane);
+    const int my_first = (int)rank * slice;
+    const int valid = max(0, min(slice, cells - my_first));  // cells this CTA owns
+    const int n_clusters = gridDim.x / CS;
+
+    for (int b = blockIdx.x / CS; b < B; b += n_clusters) {
+        // ---- phase 0: clear the slice
+        for (int i = tid; i < slice / 4; i += kClusterThreads) reinterpret_cast<float4 *>(sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cluster.sync();
+
+        // ---- phase 1: this CTA's share of the window's events -> DSMEM scatter
+        const int64_t begin = __ldg(off + b), end = __ldg(off + b + 1);
+        if (end > begin) {
+            Window w;
+            w.b = b; w.begin = begin; w.end = end;
+            w.t0 = __ldg(ev + 4 * begin);
+            w.span = __dsub_rn(__ldg(ev + 4 * (end - 1)), w.t0);
+            if (w.span == 0.0) w.span = 1.0;
+            const int64_t per = (end - begin + CS - 1) / CS;
+            const int64_t s = begin + (int64_t)rank * per, e = min(end, s + per);
+            constexpr int U = 4;
+            for (int64_t i0 = s + tid; i0 < e; i0 += (int64_t)U * kClusterThreads) {
+                Event evs[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const int64_t i = i0 + (int64_t)k * kClusterThreads;
+                    if (i < e) evs[k] = load_event(ev, i);
+                }
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const int64_t i = i0 + (int64_t)k * kClusterThreads;
+                    if (i >= e) break;
+                    const Binned bb = bin_event(evs[k], w, nb, H, W, flavour);
+                    if (!bb.ok) continue;
+                    float wl, wr;
+                    if (flavour == CF_FLAVOUR_TORCH) {
+                        weights_f32(bb, wl, wr);
+                    } else {
+                        double dl, dr;
+                        weights_f64(bb, dl, dr);
+                        wl = (float)dl;
+                        wr = (float)dr;
+                    }
+                    const int cell = (int)(((int64_t)bb.bin * planes + bb.chan) * plane + (int64_t)bb.y * W + bb.x);
+                    const unsigned own = (unsigned)cell / (unsigned)slice;
+                    red_add_cluster(sm + (cell - (int)own * slice), own, wl);
+                    if (bb.bin + 1 < nb) {
+                        const int cell2 = cell + (int)(planes * plane);
+                        const unsigned own2 = (unsigned)cell2 / (unsigned)slice;
+                        red_add_cluster(sm + (cell2 - (int)own2 * slice), own2, wr);
+                    }
+                }
+            }
+        }
+        cluster.sync();
+
+        // ---- phase 2: statistics of the slice, exchanged through DSMEM (fixed order => every
+        //      CTA of the cluster derives bit-identical mean / scale)
+        double a = 0.0, inv = 1.0;
+        bool identity = true;
+        if (preprocess != CF_PRE_NONE) {
+            double sum = 0.0, sumsq = 0.0;
+            long long nnz = 0;
+            float mn = INFINITY, mx = -INFINITY;
+            for (int i = tid; i < valid; i += kClusterThreads) {
+                const float v = hot_filter(sm[i], hot_thr);
+                sum += (double)v;
+                sumsq += (double)v * (double)v;
+                nnz += (v != 0.f);
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+            }
+            sum = warp_sum(sum); sumsq = warp_sum(sumsq); nnz = warp_sum(nnz);
+            mn = warp_min(mn); mx = warp_max(mx);
+            if (lane == 0) warp_part[warp] = Partial{sum, sumsq, nnz, mn, mx};
+            __syncthreads();
+            if (tid == 0) {
+                Partial t = warp_part[0];
+                for (int k = 1; k < kClusterThreads / 32; ++k) {
+                    t.sum += warp_part[k].sum; t.sumsq += warp_part[k].sumsq; t.nnz += warp_part[k].nnz;
+                    t.mn = fminf(t.mn, warp_part[k].mn); t.mx = fmaxf(t.mx, warp_part[k].mx);
+                }
+                *part = t;
+            }
+            cluster.sync();
+            if (warp == 0) {
+                double ts = 0.0, tq = 0.0;
+                long long tn = 0;
+                float tmn = INFINITY, tmx = -INFINITY;
+                if ((unsigned)lane < CS) {
+                    const Partial *rp = cluster.map_shared_rank(part, lane);
+                    ts = rp->sum; tq = rp->sumsq; tn = rp->nnz; tmn = rp->mn; tmx = rp->mx;
+                }
+                ts = warp_sum(ts); tq = warp_sum(tq); tn = warp_sum(tn);
+                tmn = warp_min(tmn); tmx = warp_max(tmx);
+                if (lane == 0) {
+                    if (preprocess == CF_PRE_STD) {
+                        s_identity = tn == 0;
+                        const double mean = tn ? ts / (double)tn : 0.0;
+                        const double var = tn ? tq / (double)tn - mean * mean : 0.0;
+                        s_a = mean;
+                        s_inv = 1.0 / (sqrt(fmax(var, 0.0)) + 1e-8);
+                    } else {
+                        s_identity = 0;
+                        s_a = (double)tmn;
+                        s_inv = 1.0 / ((double)tmx - (double)tmn + 1e-8);
+                    }
+                }
+            }
+            __syncthreads();
+            a = s_a; inv = s_inv; identity = s_identity != 0;
+        }
+
+        // ---- phase 3: normalise the slice and write it once
+        auto norm = [&](float raw) -> float {
+            if (preprocess == CF_PRE_NONE) return raw;
+            const float v = hot_filter(raw, hot_thr);
+            if (identity) return v;
+            if (preprocess == CF_PRE_STD) return (v != 0.f) ? (float)(((double)v - a) * inv) : 0.f;
+            return (float)(((double)v - a) * inv);
+        };
+        float *o = out + (int64_t)b * cells + my_first;
+        if ((cells & 3) == 0) {
+            for (int i = tid; i < valid / 4; i += kClusterThreads) {
+                const float4 q = reinterpret_cast<const float4 *>(sm)[i];
+                st_cs4(reinterpret_cast<float4 *>(o) + i, make_float4(norm(q.x), norm(q.y), norm(q.z), norm(q.w)));
+            }
+        } else {
+            for (int i = tid; i < valid; i += kClusterThreads) st_cs(o + i, norm(sm[i]));
+        }
+        // the next window's phase-0 cluster.sync() orders these reads before any remote add
+        __syncthreads();
+    }
+    cluster.sync();  // no CTA may exit while a peer can still address its shared memory
 }
 
 // ------------------------------------------------------ deterministic mode ---
@@ -337,16 +525,8 @@ det_accumulate_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restr
 }
 
 // ---------------------------------------------- statistics + normalisation ---
-struct alignas(16) Partial {
-    double sum, sumsq;
-    long long nnz;
-    float mn, mx;
-};
-
 constexpr int kStatThreads = 256;
 constexpr int kMaxChunks = 256;
-
-__device__ __forceinline__ float hot_filter(float v, float thr) { return (thr > 0.f && fabsf(v) > thr) ? 0.f : v; }
 
 __global__ void __launch_bounds__(kStatThreads)
 voxel_stats_kernel(const float *__restrict__ grid, int64_t cells, int64_t chunk_len, float hot_thr,
@@ -478,6 +658,67 @@ static int run_preprocess(const float *in, float *out, int B, int64_t cells, int
     return CF_OK;
 }
 
+// CF_VOXEL_FLAGS (debug / experiments): bit1 = use the cluster / DSMEM-atomics path, bit0 = do not chunk
+static int voxel_flags() {
+    static int flags = -1;
+    if (flags < 0) {
+        const char *e = getenv("CF_VOXEL_FLAGS");
+        flags = e ? atoi(e) : 0;
+    }
+    return flags;
+}
+
+// Returns CF_OK / an error, or 1 when the window grid does not fit a 16-CTA cluster's shared memory.
+static int launch_cluster_path(const double *events, const int64_t *offsets, int B, int nb, int H, int W, int flavour,
+                               int preprocess, float hot_thr, float *out, int64_t cells, cudaStream_t stream) {
+    constexpr size_t kMaxSlice = 200 * 1024;  // bytes of grid per CTA
+    if (cells * sizeof(float) > 16 * kMaxSlice || cells >= (1ll << 30)) return 1;
+    // smallest power-of-two cluster that holds the grid; grow it while the launch would leave SMs idle
+    int cs = 1;
+    while ((size_t)ceil_div(cells, cs) * sizeof(float) > kMaxSlice) cs *= 2;
+    const int sms = sm_count();
+    while (cs < 16 && (int64_t)B * cs * 2 <= sms && ceil_div(cells, cs * 2) >= 4096) cs *= 2;
+    if (const char *force = getenv("CF_VOXEL_CS")) {  // experiments: force the cluster size (must still fit)
+        const int f = atoi(force);
+        if (f >= cs && f <= 16 && (f & (f - 1)) == 0) cs = f; else if (f > 0 && f < cs) return 1;
+    }
+    const int slice = (int)((ceil_div(cells, cs) + 3) & ~(int64_t)3);
+    const size_t smem = (size_t)slice * sizeof(float) + sizeof(Partial);
+    int dev = 0;
+    CF_CUDA(cudaGetDevice(&dev));
+    static bool configured[64] = {};
+    if (!configured[dev & 63]) {
+        CF_CUDA(cudaFuncSetAttribute(voxel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxSlice + 1024)));
+        CF_CUDA(cudaFuncSetAttribute(voxel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        configured[dev & 63] = true;
+    }
+    const int per_sm = (int)((227 * 1024) / (smem + 1024));
+    int64_t max_clusters = (int64_t)(sms / cs) * (per_sm < 1 ? 1 : per_sm);
+    if (cs == 16) max_clusters = 8 * (per_sm < 1 ? 1 : per_sm);  // one 16-CTA cluster per GPC
+    if (max_clusters < 1) max_clusters = 1;
+    const int n_clusters = (int)(B < max_clusters ? B : max_clusters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * cs));
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, voxel_cluster_kernel, events, offsets, B, nb, H, W, flavour, preprocess, hot_thr,
+                                       out, slice);
+    count_launch();
+    if (e != cudaSuccess) {
+        set_error("launch of voxel_cluster_kernel (cluster %d, %zu B smem) failed: %s", cs, smem, cudaGetErrorString(e));
+        return CF_ERR_CUDA;
+    }
+    return CF_OK;
+}
+
 static int radix_bits(uint64_t max_key) {
     int bits = 1;
     while (bits < 32 && (max_key >> bits) != 0) ++bits;
@@ -543,13 +784,48 @@ extern "C" int cf_voxel_bin(const double *events, const int64_t *offsets, int64_
     cudaStream_t stream = (cudaStream_t)stream_;
     const int planes = flavour == CF_FLAVOUR_POL ? 2 : 1;
     const int64_t cells = (int64_t)nb * planes * H * W;
+    if (mode == CF_VOXEL_ATOMIC && (voxel_flags() & 2)) {  // experimental, see the file header
+        int rc = launch_cluster_path(events, offsets, B, nb, H, W, flavour, preprocess, hot_thr, out, cells, stream);
+        if (rc != 1) return rc;  // 1 = grid too large for the cluster path -> global path below
+    }
+    if (mode == CF_VOXEL_ATOMIC) {
+        // Chunks of windows that stay L2-resident from the zero-fill to the normalised write-back.
+        // The host does not know the per-window event counts (offsets live on the device), so the
+        // events of a chunk are budgeted with the batch average; kernels take device offsets.
+        const size_t per_window = (size_t)cells * sizeof(float) + (size_t)(total / B + 1) * 32;
+        int chunk = (voxel_flags() & 1) ? B : (int)((48ull << 20) / per_window);
+        if (chunk < 1) chunk = 1;
+        if (chunk > B) chunk = B;
+        if (preprocess != CF_PRE_NONE) {
+            CF_REQUIRE(ws && ws_bytes >= (size_t)B * kMaxChunks * sizeof(Partial), CF_ERR_WORKSPACE,
+                       "cf_voxel_bin: workspace too small (%zu < %zu)", ws_bytes, (size_t)B * kMaxChunks * sizeof(Partial));
+            CF_REQUIRE(aligned16(ws), CF_ERR_ALIGN, "cf_voxel_bin: workspace not 16-byte aligned");
+        }
+        for (int b0 = 0; b0 < B; b0 += chunk) {
+            const int nbat = B - b0 < chunk ? B - b0 : chunk;
+            float *o = out + (size_t)b0 * cells;
+            CF_CUDA(cudaMemsetAsync(o, 0, sizeof(float) * (size_t)nbat * cells, stream));
+            if (total > 0) {
+                // grid sized for the chunk's expected share of the events, capped at 8 CTAs per SM;
+                // the kernel grid-strides, so a longer-than-average chunk is still fully processed
+                int64_t blocks = ceil_div(ceil_div(total * nbat, B), kScatterThreads * kScatterUnroll);
+                const int64_t cap = (int64_t)sm_count() * 8;
+                if (blocks > cap) blocks = cap;
+                if (blocks < 1) blocks = 1;
+                voxel_scatter_atomic_kernel<<<(unsigned)blocks, kScatterThreads, 0, stream>>>(
+                    events, offsets, B, nb, H, W, flavour, out, b0, b0 + nbat);
+                CF_LAUNCH_CHECK("voxel_scatter_atomic_kernel");
+            }
+            if (preprocess != CF_PRE_NONE) {
+                if (int rc = run_preprocess(o, o, nbat, cells, preprocess, hot_thr,
+                                            reinterpret_cast<char *>(ws) + (size_t)b0 * kMaxChunks * sizeof(Partial),
+                                            ws_bytes - (size_t)b0 * kMaxChunks * sizeof(Partial), stream)) return rc;
+            }
+        }
+        return CF_OK;
+    }
     CF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * cells, stream));
-
-    if (total > 0 && mode == CF_VOXEL_ATOMIC) {
-        const int64_t blocks = ceil_div(total, kScatterThreads * kScatterUnroll);
-        voxel_scatter_atomic_kernel<<<(unsigned)blocks, kScatterThreads, 0, stream>>>(events, offsets, total, B, nb, H, W, flavour, out);
-        CF_LAUNCH_CHECK("voxel_scatter_atomic_kernel");
-    } else if (total > 0) {
+    if (total > 0) {
         const uint64_t columns = (uint64_t)B * planes * H * W;  // invalid key == columns
         CF_REQUIRE(columns < 0xffffffffull, CF_ERR_INVALID_ARG, "cf_voxel_bin: B*H*W too large for the deterministic mode");
         const size_t base = align_up(cf_preprocess_workspace_bytes(B, 0), 256);

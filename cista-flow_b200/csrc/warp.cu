@@ -17,132 +17,13 @@
 // batches of CPT channels with all 4*CPT loads in flight before the first FMA.
 // No fast-math in this file: the position arithmetic mirrors ATen's operation
 // order (true fp32 division) so that floor() picks the same taps.
-#include "common.cuh"
+#include "warp_common.cuh"
 
 namespace cf {
 
-struct Taps {
-    int o00, o01, o10, o11;  // offsets inside one channel plane
-    float w00, w01, w10, w11;
-};
-
-// ATen reflect_coordinates(v, 0, 2*(size-1)) followed by clip_coordinates.
-__device__ __forceinline__ float reflect_clip(float v, int size) {
-    if (size == 1) return 0.f;
-    const float span = (float)(size - 1);
-    const float a = fabsf(v);
-    const float extra = fmodf(a, span);
-    const int flips = (int)floorf(a / span);
-    const float r = (flips & 1) ? span - extra : extra;
-    return fminf(span, fmaxf(r, 0.f));
-}
-
-// Flow at output pixel (x, y).  half == false: flow has the output's size.
-// half == true: x0.5 bilinear, align_corners=True from the [fH, fW] field
-// (ATen upsample_bilinear2d: src = scale*dst, lambda clamped to [0,1]).
-__device__ __forceinline__ float2 flow_at(const float *__restrict__ fb, int x, int y, int W,
-                                          int fH, int fW, bool half, float sy, float sx) {
-    if (!half) {
-        const int p = y * W + x;
-        return make_float2(__ldg(fb + p), __ldg(fb + (size_t)fH * fW + p));
-    }
-    const float fy = sy * (float)y, fx = sx * (float)x;
-    int y0 = min((int)fy, fH - 1), x0 = min((int)fx, fW - 1);
-    const int y1 = y0 + (y0 < fH - 1 ? 1 : 0), x1 = x0 + (x0 < fW - 1 ? 1 : 0);
-    const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
-    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-    float2 r;
-    const float *c = fb;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const float p00 = __ldg(c + y0 * fW + x0), p01 = __ldg(c + y0 * fW + x1);
-        const float p10 = __ldg(c + y1 * fW + x0), p11 = __ldg(c + y1 * fW + x1);
-        const float v = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
-        if (k == 0) r.x = v; else r.y = v;
-        c += (size_t)fH * fW;
-    }
-    return r;
-}
-
-__device__ __forceinline__ Taps make_taps(float u, float v, int x, int y, int H, int W, float sign) {
-    // utils/flow_utils.py:110-116 (sign=+1) / :180-186 (sign=-1), then ATen
-    // grid_sampler_unnormalize(align_corners=True): ((g + 1) / 2) * (size - 1).
-    const float gx = 2.f * (((float)x + sign * u) / (float)W - 0.5f);
-    const float gy = 2.f * (((float)y + sign * v) / (float)H - 0.5f);
-    const float ix = reflect_clip(((gx + 1.f) / 2.f) * (float)(W - 1), W);
-    const float iy = reflect_clip(((gy + 1.f) / 2.f) * (float)(H - 1), H);
-    const float fx0 = floorf(ix), fy0 = floorf(iy);
-    const int x0 = (int)fx0, y0 = (int)fy0;
-    // after the clip x0+1 == W only when ix == W-1 exactly, where its weight is 0
-    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-    // ATen weights: nw = (x_se - ix)(y_se - iy), ne = (ix - x_sw)(y_sw - iy), ...
-    const float ax1 = (fx0 + 1.f) - ix, ax0 = ix - fx0;
-    const float ay1 = (fy0 + 1.f) - iy, ay0 = iy - fy0;
-    Taps t;
-    t.o00 = y0 * W + x0; t.o01 = y0 * W + x1; t.o10 = y1 * W + x0; t.o11 = y1 * W + x1;
-    t.w00 = ax1 * ay1;
-    t.w01 = ax0 * ay1;
-    t.w10 = ax1 * ay0;
-    t.w11 = ax0 * ay0;
-    return t;
-}
-
-// One thread = one output pixel x CPT channels.
-template <int CPT>
-__device__ __forceinline__ void warp_pixel(const float *__restrict__ img_b, float *__restrict__ out_b,
-                                           const Taps &t, int p, int c0, int C, size_t plane) {
-    float v[CPT][4];
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        const int c = c0 + k;
-        if (c < C) {
-            const float *s = img_b + (size_t)c * plane;
-            v[k][0] = __ldg(s + t.o00); v[k][1] = __ldg(s + t.o01);
-            v[k][2] = __ldg(s + t.o10); v[k][3] = __ldg(s + t.o11);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        const int c = c0 + k;
-        if (c < C) {
-            // ATen order: nw, ne, sw, se accumulated left to right
-            float r = v[k][0] * t.w00;
-            r += v[k][1] * t.w01;
-            r += v[k][2] * t.w10;
-            r += v[k][3] * t.w11;
-            st_cs(out_b + (size_t)c * plane + p, r);
-        }
-    }
-}
-
-struct WarpJob {
-    const float *img; float *out;
-    int C, H, W;          // geometry of img/out
-    int half;             // 1: flow is [2, fH, fW] at twice the resolution
-    float sy, sx;         // align_corners scales for the fused down-sampling
-    int tiles_x;          // 32-pixel-wide tiles per row
-    int blocks_x;         // pixel tiles (32x8) per (batch, channel group)
-    int cpg;              // channels per group (one thread loops over them, CPT at a time)
-    int groups;           // channel groups
-};
-constexpr int kTileW = 32, kTileH = 8;
-
-template <int CPT>
-__device__ __forceinline__ void run_job(const WarpJob &j, const float *__restrict__ flow,
-                                        int fH, int fW, float sign, int tile, int group, int b) {
-    const int ty = tile / j.tiles_x, tx = tile - ty * j.tiles_x;
-    const int x = tx * kTileW + (threadIdx.x & 31), y = ty * kTileH + (threadIdx.x >> 5);
-    if (x >= j.W || y >= j.H) return;
-    const int p = y * j.W + x;
-    const float *fb = flow + (size_t)b * 2 * fH * fW;
-    const float2 uv = flow_at(fb, x, y, j.W, fH, fW, j.half != 0, j.sy, j.sx);
-    const Taps t = make_taps(uv.x, uv.y, x, y, j.H, j.W, sign);
-    const size_t plane = (size_t)j.H * j.W;
-    const float *img_b = j.img + (size_t)b * j.C * plane;
-    float *out_b = j.out + (size_t)b * j.C * plane;
-    const int c_end = min(j.C, (group + 1) * j.cpg);
-    for (int c0 = group * j.cpg; c0 < c_end; c0 += CPT) warp_pixel<CPT>(img_b, out_b, t, p, c0, c_end, plane);
-}
+// implemented in warp_tma.cu: CF_OK / error, or 1 when the TMA-staged path does not apply
+int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const float *flow, int fH, int fW, float sign,
+                    int B, cudaStream_t stream);
 
 template <int CPT>
 __global__ void __launch_bounds__(256, 4) warp_gather_kernel(WarpJob j, const float *__restrict__ flow,
@@ -203,6 +84,10 @@ extern "C" int cf_warp(const float *img, const float *flow, float *out, int B, i
     WarpJob j;
     if (int rc = make_job(j, img, out, C, H, W, flowH, flowW, cpt)) return rc;
     CF_REQUIRE(j.groups <= 65535, CF_ERR_INVALID_ARG, "cf_warp: too many channels");
+    if (C >= 8) {  // multi-channel tensors: TMA-staged kernel when the shape allows it
+        const int rc = launch_warp_tma(j, false, j, flow, flowH, flowW, sign, B, stream);
+        if (rc != 1) return rc;
+    }
     dim3 grid(j.blocks_x, j.groups, B);
     if (cpt == 8) warp_gather_kernel<8><<<grid, 256, 0, stream>>>(j, flow, flowH, flowW, sign);
     else if (cpt == 4) warp_gather_kernel<4><<<grid, 256, 0, stream>>>(j, flow, flowH, flowW, sign);
@@ -226,6 +111,10 @@ extern "C" int cf_warp_frame_and_codes(const float *img, const float *codes, con
     WarpJob ji, jz;
     if (int rc = make_job(ji, img, img_out, Ci, H, W, H, W, 1)) return rc;
     if (int rc = make_job(jz, codes, codes_out, Cz, H / 2, W / 2, H, W, 8)) return rc;
+    {
+        const int rc = launch_warp_tma(ji, true, jz, flow, H, W, sign, B, stream);
+        if (rc != 1) return rc;
+    }
     dim3 grid(ji.blocks_x * ji.groups + jz.blocks_x * jz.groups, B);
     warp_frame_and_codes_kernel<<<grid, 256, 0, stream>>>(ji, jz, flow, H, W, sign);
     CF_LAUNCH_CHECK("warp_frame_and_codes_kernel");
