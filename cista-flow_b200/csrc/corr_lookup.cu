@@ -57,7 +57,6 @@ corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict_
     const int b = blockIdx.y;
     const int q0 = blockIdx.x * QT;
     const float *cb = coords + (size_t)b * 2 * N;
-
     if (tid < QT) {
         const int q = q0 + tid;
         // clamp keeps (int) conversions defined for wild coordinates; anything
@@ -216,6 +215,8 @@ static int launch_lookup(const Pyramid &pyr, const float *coords, float *out, in
         opt_in[dev & 63] = true;
     }
     dim3 grid((unsigned)ceil_div(N, QT), B);
+    // (programmatic dependent launch was tried here: with 12 lookups back to back in a graph it made
+    //  each launch 1.4 us SLOWER on the B200 -- 8.8 vs 7.4 us -- so plain stream order is kept)
     corr_lookup_kernel<RADIUS, LEVELS, QT><<<grid, kLookupThreads, smem, stream>>>(pyr, coords, out, N, levels, radius);
     CF_LAUNCH_CHECK("corr_lookup_kernel");
     return CF_OK;
