@@ -32,6 +32,7 @@ SYMBOLS = {
     "cf_last_error": (ctypes.c_char_p, []),
     "cf_device_check": (_i, []),
     "cf_launch_count": (_i64, []),
+    "cf_last_kernel": (ctypes.c_char_p, []),
     "cf_voxel_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i, _i, _i, _i]),
     "cf_voxel_bin": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _sz, _vp]),
     "cf_preprocess_workspace_bytes": (_sz, [_i, _i64]),

@@ -35,7 +35,8 @@ def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.float().contiguous()
 
 
-def build_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4, precision: str | None = None):
+def build_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4, precision: str | None = None,
+                  out: list[torch.Tensor] | None = None):
     fmap1, fmap2 = _prep(fmap1, "fmap1"), _prep(fmap2, "fmap2")
     assert fmap1.shape == fmap2.shape and fmap1.dim() == 4
     B, D, h, w = fmap1.shape
@@ -44,7 +45,14 @@ def build_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4,
     if prec == "tf32" and (D % 32 != 0 or (h * w) % 4 != 0):
         prec = "fp32"  # shapes the tensor-core tiling does not cover (never the model's: D=256, h,w % 4 == 0)
     dev = fmap1.device
-    pyramid = [torch.empty((B * h * w, 1, h >> l, w >> l), dtype=torch.float32, device=dev) for l in range(num_levels)]
+    shapes = [(B * h * w, 1, h >> l, w >> l) for l in range(num_levels)]
+    if out is None:
+        pyramid = [torch.empty(s, dtype=torch.float32, device=dev) for s in shapes]
+    else:
+        pyramid = list(out)
+        assert len(pyramid) == num_levels
+        for t, s in zip(pyramid, shapes):
+            assert tuple(t.shape) == s and t.dtype == torch.float32 and t.is_contiguous() and t.device == dev
     with torch.cuda.device(dev):
         ws_bytes = lib.cf_corr_workspace_bytes(B, D, h, w, num_levels, _PREC[prec])
         ws = _lib.workspace(ws_bytes, dev)

@@ -11,7 +11,12 @@ namespace cf {
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static thread_local const char *g_last_kernel = "";
+
+void count_launch(const char *kernel) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_last_kernel = kernel;
+}
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -74,5 +79,7 @@ const char *cf_last_error(void) { return cf::g_err; }
 int cf_device_check(void) { return cf::check_device(); }
 
 int64_t cf_launch_count(void) { return cf::g_launches.load(std::memory_order_relaxed); }
+
+const char *cf_last_kernel(void) { return cf::g_last_kernel; }
 
 }  // extern "C"

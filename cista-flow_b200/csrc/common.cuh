@@ -13,7 +13,7 @@ namespace cf {
 void set_error(const char *fmt, ...);
 int check_device();  // CF_OK or CF_ERR_ARCH/CF_ERR_CUDA (cached per device)
 int sm_count();      // SM count of the current device (148 on B200)
-void count_launch(); // bumps the counter behind cf_launch_count()
+void count_launch(const char *kernel); // bumps cf_launch_count(), remembers the name for cf_last_kernel()
 
 #define CF_REQUIRE(cond, code, ...)      \
     do {                                 \
@@ -35,7 +35,7 @@ void count_launch(); // bumps the counter behind cf_launch_count()
 
 #define CF_LAUNCH_CHECK(name)                                                           \
     do {                                                                                \
-        cf::count_launch();                                                             \
+        cf::count_launch(name);                                                             \
         cudaError_t e__ = cudaGetLastError();                                           \
         if (e__ != cudaSuccess) {                                                       \
             cf::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));    \

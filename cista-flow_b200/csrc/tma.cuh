@@ -34,6 +34,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         if (++spins > (1u << 26)) __trap();
     }
 }
+// one lane polls (with back-off), the warp re-converges behind it: 32 lanes spinning on try_wait
+// compete with the working warps for the shared-memory pipe (measured: scripts/warp_trace.py)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+    if ((threadIdx.x & 31u) == 0) {
+        uint32_t spins = 0;
+        while (!mbar_try_wait(bar, parity)) {
+            if (++spins > 8) __nanosleep(spins > 64 ? 256 : 32);
+            if (spins > (1u << 24)) __trap();
+        }
+    }
+    __syncwarp();
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

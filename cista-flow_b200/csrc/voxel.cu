@@ -711,7 +711,7 @@ static int launch_cluster_path(const double *events, const int64_t *offsets, int
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, voxel_cluster_kernel, events, offsets, B, nb, H, W, flavour, preprocess, hot_thr,
                                        out, slice);
-    count_launch();
+    count_launch("voxel_cluster_kernel");
     if (e != cudaSuccess) {
         set_error("launch of voxel_cluster_kernel (cluster %d, %zu B smem) failed: %s", cs, smem, cudaGetErrorString(e));
         return CF_ERR_CUDA;

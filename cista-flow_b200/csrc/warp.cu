@@ -25,6 +25,11 @@ namespace cf {
 int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const float *flow, int fH, int fW, float sign,
                     int B, cudaStream_t stream);
 
+static int launch_staged(const WarpJob &ji, bool with_image, const WarpJob &jz, const float *flow, int fH, int fW,
+                         float sign, int B, cudaStream_t stream) {
+    return launch_warp_tma(ji, with_image, jz, flow, fH, fW, sign, B, stream);
+}
+
 template <int CPT>
 __global__ void __launch_bounds__(256, 4) warp_gather_kernel(WarpJob j, const float *__restrict__ flow,
                                                           int fH, int fW, float sign) {
@@ -85,7 +90,7 @@ extern "C" int cf_warp(const float *img, const float *flow, float *out, int B, i
     if (int rc = make_job(j, img, out, C, H, W, flowH, flowW, cpt)) return rc;
     CF_REQUIRE(j.groups <= 65535, CF_ERR_INVALID_ARG, "cf_warp: too many channels");
     if (C >= 8) {  // multi-channel tensors: TMA-staged kernel when the shape allows it
-        const int rc = launch_warp_tma(j, false, j, flow, flowH, flowW, sign, B, stream);
+        const int rc = launch_staged(j, false, j, flow, flowH, flowW, sign, B, stream);
         if (rc != 1) return rc;
     }
     dim3 grid(j.blocks_x, j.groups, B);
@@ -112,7 +117,7 @@ extern "C" int cf_warp_frame_and_codes(const float *img, const float *codes, con
     if (int rc = make_job(ji, img, img_out, Ci, H, W, H, W, 1)) return rc;
     if (int rc = make_job(jz, codes, codes_out, Cz, H / 2, W / 2, H, W, 8)) return rc;
     {
-        const int rc = launch_warp_tma(ji, true, jz, flow, H, W, sign, B, stream);
+        const int rc = launch_staged(ji, true, jz, flow, H, W, sign, B, stream);
         if (rc != 1) return rc;
     }
     dim3 grid(ji.blocks_x * ji.groups + jz.blocks_x * jz.groups, B);

@@ -13,9 +13,22 @@
 //   3. the threads gather their 4 taps from shared memory (conflict-free: consecutive lanes read
 //      consecutive columns) and write 128-byte rows with streaming stores.
 //   Tiles whose box does not fit (flow discontinuities) fall back to the direct gather in place.
+// Variants measured on the B200 and NOT adopted (scripts/scale_bench.py; round-1 notes in DESIGN.md):
+//   * persistent warp-specialised kernel, one CTA per SM, producer warps + mbarrier ring + consumer
+//     warps (scripts/experiments/warp_persist.cu): 18-30 % -- with 8-16 consumer warps per SM the
+//     per-chunk issue latency (2-4 warps per scheduler, i-cache misses of three code roles, and, under
+//     a tight register cap, local-memory spills that miss the ~10 KB of L1 left beside a 215 KB ring)
+//     bounds it, not memory (timelines: scripts/warp_trace.py);
+//   * per-row cp.async.bulk (UBLKCP) for shapes without a 16-byte row pitch: ~70 cycles per issued
+//     copy, serialised per lane;
+//   * 64x16 tiles + a 3x3 menu of tensor-map boxes (over-fetch 1.3x instead of 2.25x), 2 CTAs per SM:
+//     28 % / 42 % against 44 % / 57 % for this kernel at 180x240 / 480x640 -- occupancy (3 small CTAs,
+//     2 pixels per thread) beats bytes saved.
 // The optional image part (1 channel, full resolution) of the per-frame step rides in the same
 // launch through the direct path.  Needs a 16-byte aligned row pitch (W % 4 == 0) for the tensor
 // map; other shapes use warp.cu.
+#include <string.h>
+
 #include "tma.cuh"
 #include "warp_common.cuh"
 
@@ -28,7 +41,7 @@ constexpr int CC = 8;                    // channels per stage
 constexpr int STAGES = 2;
 constexpr int STAGE_FLOATS = CC * BH * BW;
 constexpr int STAGE_BYTES = STAGE_FLOATS * 4;              // 36 864
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128 + 64;  // + alignment slack + barriers
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 64;  // + barriers
 constexpr int CH_PER_CTA = 32;           // channel group of one CTA (4 stages of work)
 }  // namespace wt
 
@@ -38,16 +51,57 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_
     using namespace wt;
     const int b = blockIdx.y;
     int blk = blockIdx.x;
-    if (blk < n_img_blocks) {  // image part: direct gather
-        run_job<1>(ji, flow, fH, fW, sign, blk % ji.blocks_x, blk / ji.blocks_x, b);
+    const int n_codes_blocks = tiles * groups;
+    if (blk >= n_codes_blocks) {
+        // image part (after the codes blocks in launch order: it fills the partial last wave).  One CTA =
+        // a 32x32 pixel region, thread <-> 4 rows: all flow loads, then all 16 tap loads, then the stores
+        // (one pixel per thread cost two dependent DRAM round trips per 256 pixels: 8 of 32 us at 180x240)
+        blk -= n_codes_blocks;
+        const int itx = (ji.W + 31) / 32;
+        const int ity = blk / itx, itxx = blk - ity * itx;
+        const int Hi = ji.H, Wi = ji.W;
+        const size_t hw = (size_t)Hi * Wi;
+        const float *fbi = flow + (size_t)b * 2 * fH * fW;  // image resolution == flow resolution
+        const int x = itxx * 32 + (threadIdx.x & 31);
+        const int xc = min(x, Wi - 1);
+        int yy[4];
+        float fu[4], fv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            yy[k] = ity * 32 + (int)(threadIdx.x >> 5) + 8 * k;
+            const int yc = min(yy[k], Hi - 1);
+            fu[k] = __ldg(fbi + (size_t)yc * Wi + xc);
+            fv[k] = __ldg(fbi + hw + (size_t)yc * Wi + xc);
+        }
+        Taps t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = make_taps(fu[k], fv[k], xc, min(yy[k], Hi - 1), Hi, Wi, sign);
+        for (int c = 0; c < ji.C; ++c) {
+            const float *src = ji.img + ((size_t)b * ji.C + c) * hw;
+            float *dst = ji.out + ((size_t)b * ji.C + c) * hw;
+            float v[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k][0] = __ldg(src + t[k].o00); v[k][1] = __ldg(src + t[k].o01);
+                v[k][2] = __ldg(src + t[k].o10); v[k][3] = __ldg(src + t[k].o11);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float r = v[k][0] * t[k].w00;
+                r += v[k][1] * t[k].w01;
+                r += v[k][2] * t[k].w10;
+                r += v[k][3] * t[k].w11;
+                if (x < Wi && yy[k] < Hi) st_cs(dst + (size_t)yy[k] * Wi + x, r);
+            }
+        }
         return;
     }
-    blk -= n_img_blocks;
     const int group = blk / tiles, tile = blk - group * tiles;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
 
-    extern __shared__ uint8_t smem_raw[];
-    float *stage0 = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    // declared aligned, no run-time rounding: keeps the pointers in the shared address space (LDS, not generic LD.E)
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float *stage0 = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(stage0 + STAGES * STAGE_FLOATS);
     __shared__ int s_box[4];   // min x0, min y0, max x1, max y1
     __shared__ int red[4][8];
@@ -150,25 +204,22 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_
             float *o = out_b + (size_t)c0 * plane + (size_t)(ty * TH + warp + 8 * j) * W + x;
             const float *s0 = st + s00[j], *s1 = st + s01[j], *s2 = st + s10[j], *s3 = st + s11[j];
             const float w0 = taps[j].w00, w1 = taps[j].w01, w2 = taps[j].w10, w3 = taps[j].w11;
-            if (full_chunk) {
+            float v[CC][4];  // all 32 tap loads before the first store (LDS/STG interleaving serialises on aliasing)
 #pragma unroll
-                for (int c = 0; c < CC; ++c) {
-                    float r = s0[c * (BH * BW)] * w0;
-                    r += s1[c * (BH * BW)] * w1;
-                    r += s2[c * (BH * BW)] * w2;
-                    r += s3[c * (BH * BW)] * w3;
-                    st_cs(o, r);
-                    o += plane;
-                }
-            } else {
-                for (int c = 0; c0 + c < c_end; ++c) {
-                    float r = s0[c * (BH * BW)] * w0;
-                    r += s1[c * (BH * BW)] * w1;
-                    r += s2[c * (BH * BW)] * w2;
-                    r += s3[c * (BH * BW)] * w3;
-                    st_cs(o, r);
-                    o += plane;
-                }
+            for (int c = 0; c < CC; ++c) {
+                v[c][0] = s0[c * (BH * BW)];
+                v[c][1] = s1[c * (BH * BW)];
+                v[c][2] = s2[c * (BH * BW)];
+                v[c][3] = s3[c * (BH * BW)];
+            }
+#pragma unroll
+            for (int c = 0; c < CC; ++c) {
+                float r = v[c][0] * w0;
+                r += v[c][1] * w1;
+                r += v[c][2] * w2;
+                r += v[c][3] * w3;
+                if (full_chunk || c0 + c < c_end) st_cs(o, r);
+                o += plane;
             }
         }
         __syncthreads();  // every thread is done with this stage before it is refilled
@@ -178,7 +229,8 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_
 int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const float *flow, int fH, int fW, float sign,
                     int B, cudaStream_t stream) {
     using namespace wt;
-    static const bool disabled = getenv("CF_WARP_NO_TMA") != nullptr;  // experiments: force the direct gather
+    static const char *env = getenv("CF_WARP_PATH");  // experiments: "direct" forces the plain gather
+    const bool disabled = env && !strcmp(env, "direct");
     if (disabled || jz.W % 4 != 0 || jz.C < CC || !aligned16(jz.img)) return 1;
     TensorMapEncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return 1;
@@ -196,11 +248,12 @@ int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const
     static bool opt_in[64] = {};
     if (!opt_in[dev & 63]) {
         CF_CUDA(cudaFuncSetAttribute(warp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CF_CUDA(cudaFuncSetAttribute(warp_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         opt_in[dev & 63] = true;
     }
     const int tiles_x = (int)ceil_div(jz.W, TW), tiles = tiles_x * (int)ceil_div(jz.H, TH);
     const int groups = (int)ceil_div(jz.C, CH_PER_CTA);
-    const int n_img = with_image ? ji.blocks_x * ji.groups : 0;
+    const int n_img = with_image ? (int)(ceil_div(ji.W, 32) * ceil_div(ji.H, 32)) : 0;
     dim3 grid((unsigned)(n_img + tiles * groups), (unsigned)B);
     warp_tma_kernel<<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, n_img, jz, tiles_x, tiles, groups, flow, fH, fW, sign);
     CF_LAUNCH_CHECK("warp_tma_kernel");

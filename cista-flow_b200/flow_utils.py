@@ -49,7 +49,8 @@ def warp(img: torch.Tensor, flow: torch.Tensor, sign: float, out: torch.Tensor |
     return out
 
 
-def warp_frame_and_codes(img: torch.Tensor, codes: torch.Tensor, flow: torch.Tensor, mode: str = "forward"):
+def warp_frame_and_codes(img: torch.Tensor, codes: torch.Tensor, flow: torch.Tensor, mode: str = "forward",
+                         out: tuple[torch.Tensor, torch.Tensor] | None = None):
     """One launch for ``e2v/e2v_model.py:188-191``: returns (warped image, warped codes).
     img [B,Ci,H,W], codes [B,Cz,H//2,W//2], flow [B,2,H,W]."""
     img, codes, flow = _prep(img, "img"), _prep(codes, "codes"), _prep(flow, "flow")
@@ -57,7 +58,12 @@ def warp_frame_and_codes(img: torch.Tensor, codes: torch.Tensor, flow: torch.Ten
     assert flow.shape == (B, 2, H, W), "flow must be [B,2,H,W] at the image resolution"
     assert codes.shape[0] == B and codes.shape[2] == H // 2 and codes.shape[3] == W // 2, \
         "codes must be [B,C,H//2,W//2]"
-    img_out, codes_out = torch.empty_like(img), torch.empty_like(codes)
+    if out is None:
+        img_out, codes_out = torch.empty_like(img), torch.empty_like(codes)
+    else:
+        img_out, codes_out = out
+        for o, ref in ((img_out, img), (codes_out, codes)):
+            assert o.shape == ref.shape and o.dtype == torch.float32 and o.is_contiguous() and o.device == ref.device
     sign = -1.0 if mode == "forward" else 1.0
     lib = _lib.load()
     with torch.cuda.device(img.device):

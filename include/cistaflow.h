@@ -59,6 +59,10 @@ CF_API int cf_device_check(void);
  * capture) in this process so far; benchmarks report it as evidence that the
  * hand-written kernels -- not a fallback -- did the work. */
 CF_API int64_t cf_launch_count(void);
+/* Name of the kernel this thread launched last ("" before the first launch): lets tests assert
+ * WHICH of the data-movement variants of an entry point ran (e.g. the TMA-staged warp kernel
+ * vs the direct gather it falls back to on discontinuous flow). */
+CF_API const char *cf_last_kernel(void);
 
 /* ------------------------------------------------------------------------- *
  * Part 1: event stream -> voxel grid (+ normalisation)

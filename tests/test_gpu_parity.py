@@ -193,6 +193,57 @@ def test_warp_vs_oracle_config_shapes(cuda_device, h, w, batch, channels, mode):
     assert (frame.warp_frame(dev_t(img, cuda_device), dev_t(flow, cuda_device)).cpu() - ref_i).abs().max().item() <= 1e-4
 
 
+def last_kernel():
+    from cistaflow_b200 import _lib
+    return _lib.load().cf_last_kernel().decode()
+
+
+@pytest.mark.parametrize("h,w,batch,channels,kernel", [
+    (180, 240, 2, 128, "persist"),    # configs[1]: 90x120 codes, row pitch % 16 B == 0 -> TMA tensor boxes
+    (260, 346, 1, 128, "direct"),      # configs[2]: 130x173 codes, odd width: no 16-byte row pitch -> direct gather
+    (624, 970, 1, 24, "direct"),       # configs[3] shape (312x485 codes), fewer channels to bound the CPU oracle
+    (64, 96, 3, 13, "persist"),       # 13 channels: last chunk is partial (TMA zero-fills the missing channels)
+    (66, 102, 2, 11, "direct"),        # 33x51 codes: odd width AND plane % 4 != 0
+    (36, 40, 1, 8, "persist"),        # tile larger than the image
+])
+@pytest.mark.parametrize("mode", ["forward", "backward"])
+def test_warp_staged_paths_smooth_flow(cuda_device, h, w, batch, channels, kernel, mode):
+    """Network-like (smooth) flow: the taps of a tile fit the staging box, so the TMA-staged
+    kernel does the work (asserted through cf_last_kernel), not the direct gather."""
+    img, codes, flow = synth.warp_inputs(batch, h, w, seed=9, code_channels=channels, flow_kind="smooth")
+    ref_i, ref_z = ref_port.warp_frame_and_codes(torch.from_numpy(img), torch.from_numpy(codes), torch.from_numpy(flow), mode)
+    wi, wz = cf.warp_frame_and_codes(dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(flow, cuda_device), mode)
+    names = {"persist": ("warp_tma_kernel", "warp_tma_kernel"),
+             "direct": ("warp_frame_and_codes_kernel", "warp_gather_kernel")}[kernel]
+    assert last_kernel() == names[0]
+    assert (wi.cpu() - ref_i).abs().max().item() <= 1e-4
+    assert (wz.cpu() - ref_z).abs().max().item() <= 1e-4
+    # the generic entry point (no image part, flow already at the codes' resolution)
+    half = torch.nn.functional.interpolate(torch.from_numpy(flow), scale_factor=0.5, mode="bilinear", align_corners=True)
+    got = cf.warp(dev_t(codes, cuda_device), half.to(cuda_device), -1.0 if mode == "forward" else 1.0)
+    assert last_kernel() == names[1]
+    assert (got.cpu() - ref_z).abs().max().item() <= 1e-4
+
+
+def test_warp_staged_misaligned_base_and_mixed_tiles(cuda_device):
+    """(a) a codes tensor whose base address is only 4-byte aligned (a view into a larger buffer) cannot
+    be described by a tensor map and takes the direct gather; (b) smooth flow with one discontinuity: tiles
+    that fit use the ring, the others the in-kernel direct gather, in the same launch."""
+    B, C, H, W = 2, 16, 128, 192
+    img, codes, flow = synth.warp_inputs(B, H, W, seed=4, code_channels=C, flow_kind="smooth")
+    flow[:, :, 40:90, 60:130] += 37.0   # a moving object: taps of the tiles on its border span > 48 px
+    ref_i, ref_z = ref_port.warp_frame_and_codes(torch.from_numpy(img), torch.from_numpy(codes), torch.from_numpy(flow), "forward")
+    for shift in (0, 1, 3):
+        buf = torch.zeros(codes.size + 8, device=cuda_device)
+        view = buf[shift:shift + codes.size].view(codes.shape)
+        view.copy_(torch.from_numpy(codes))
+        assert view.data_ptr() % 16 == 4 * shift
+        wi, wz = cf.warp_frame_and_codes(dev_t(img, cuda_device), view, dev_t(flow, cuda_device), "forward")
+        assert last_kernel() == ("warp_tma_kernel" if shift == 0 else "warp_frame_and_codes_kernel")
+        assert (wi.cpu() - ref_i).abs().max().item() <= 1e-4
+        assert (wz.cpu() - ref_z).abs().max().item() <= 1e-4
+
+
 def test_warp_full_size_properties(cuda_device):
     """480x640 codes (config 5): constant image stays constant (weights sum to 1);
     linearity warp(a*x + y) = a*warp(x) + warp(y); forward(flow) == backward(-flow)."""
