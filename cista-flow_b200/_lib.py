@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CISTAFLOW_LIB", os.path.join(_HERE, "libcistaflow.so"))
 
 # enums of include/cistaflow.h
-VOXEL_ATOMIC, VOXEL_DETERMINISTIC = 0, 1
+VOXEL_ATOMIC, VOXEL_DETERMINISTIC, VOXEL_ATOMIC_L2, VOXEL_ATOMIC_TILED = 0, 1, 2, 3
 FLAVOUR_TORCH, FLAVOUR_NUMPY, FLAVOUR_POL = 0, 1, 2
 PRE_NONE, PRE_STD, PRE_MAXMIN = 0, 1, 2
 CORR_TF32, CORR_FP32, CORR_3XTF32 = 0, 1, 2

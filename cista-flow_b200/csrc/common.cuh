@@ -73,4 +73,27 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+#ifdef CF_TRACE
+// experiment builds only (build.build_variant('trace', ['CF_TRACE'])): per-CTA timelines in globaltimer ns,
+// read back by scripts/*_trace.py through cf_trace_buffer()
+// (one copy per translation unit -- no relocatable device code; each traced .cu exports its own setter)
+static __device__ unsigned long long *g_trace = nullptr;
+constexpr int kTraceSlots = 256;
+#define CF_DEFINE_TRACE_SETTER(name)                                                              \
+    extern "C" __attribute__((visibility("default"))) int name(unsigned long long *buf) {        \
+        return (int)cudaMemcpyToSymbol(cf::g_trace, &buf, sizeof(buf));                           \
+    }
+__device__ __forceinline__ void trace_at(int slot) {
+    if (g_trace && slot < kTraceSlots) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[(size_t)blockIdx.x * kTraceSlots + slot] = t;
+    }
+}
+#define CF_TRACE_AT(slot) cf::trace_at(slot)
+#else
+#define CF_TRACE_AT(slot) ((void)0)
+#define CF_DEFINE_TRACE_SETTER(name)
+#endif
+
 }  // namespace cf

@@ -35,87 +35,11 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "voxel_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace cf {
-
-// ------------------------------------------------------------------ events ---
-struct Event {
-    double t, x, y, p;
-};
-
-__device__ __forceinline__ Event load_event(const double *__restrict__ ev, int64_t i) {
-    const double2 *p = reinterpret_cast<const double2 *>(ev) + 2 * i;
-    const double2 a = __ldg(p), b = __ldg(p + 1);  // 2 x 128-bit
-    return Event{a.x, a.y, b.x, b.y};
-}
-
-struct Window {
-    int b;
-    int64_t begin, end;
-    double t0, span;
-};
-
-// Window that owns event i, starting the search from hint `w.b`.
-__device__ __forceinline__ void locate_window(Window &w, int64_t i, const int64_t *__restrict__ off,
-                                              const double *__restrict__ ev, int B) {
-    if (w.b >= 0 && i >= w.begin && i < w.end) return;
-    int lo = 0, hi = B - 1;  // last b with off[b] <= i
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(off + mid) <= i) lo = mid; else hi = mid - 1;
-    }
-    w.b = lo;
-    w.begin = __ldg(off + lo);
-    w.end = __ldg(off + lo + 1);
-    w.t0 = __ldg(ev + 4 * w.begin);
-    const double last = __ldg(ev + 4 * (w.end - 1));
-    w.span = __dsub_rn(last, w.t0);
-    if (w.span == 0.0) w.span = 1.0;  // event_process.py:43-44
-}
-
-struct Binned {
-    int bin;      // ti
-    int x, y;     // truncated coordinates
-    int chan;     // polarity channel (POL flavour)
-    double dt;    // t* - ti  (fp64)
-    double sgn;   // +-1 weight sign (p itself when p != 0)
-    bool ok;
-};
-
-__device__ __forceinline__ Binned bin_event(const Event &e, const Window &w, int nb, int H, int W, int flavour) {
-    Binned r;
-    // t* = (nb-1)*(t-t0)/dT : one rounding per operation, no contraction
-    const double tn = __ddiv_rn(__dmul_rn((double)(nb - 1), __dsub_rn(e.t, w.t0)), w.span);
-    const double lo = floor(tn);
-    r.ok = (lo >= 0.0) && (lo < (double)nb) && (e.x >= 0.0) && (e.y >= 0.0) && (e.x < (double)W) && (e.y < (double)H);
-    r.bin = r.ok ? (int)lo : 0;
-    r.x = r.ok ? (int)e.x : 0;
-    r.y = r.ok ? (int)e.y : 0;
-    r.dt = __dsub_rn(tn, lo);
-    r.chan = 0;
-    if (flavour == CF_FLAVOUR_POL) {
-        r.chan = (int)e.p;
-        r.ok = r.ok && (e.p >= 0.0) && (e.p < 2.0);
-        r.sgn = (e.p == 0.0) ? 1.0 : e.p;
-    } else {
-        r.sgn = (e.p == 0.0) ? -1.0 : e.p;
-    }
-    return r;
-}
-
-// left/right weights exactly as the reference forms them
-__device__ __forceinline__ void weights_f32(const Binned &b, float &wl, float &wr) {
-    const float s = (float)b.sgn, f = (float)b.dt;  // event_process.py:163,169-170
-    wl = __fmul_rn(s, __fsub_rn(1.0f, f));
-    wr = __fmul_rn(s, f);
-}
-__device__ __forceinline__ void weights_f64(const Binned &b, double &wl, double &wr) {
-    wl = __dmul_rn(b.sgn, __dsub_rn(1.0, b.dt));  // event_process.py:58-59
-    wr = __dmul_rn(b.sgn, b.dt);
-}
 
 // ------------------------------------------------------------ atomic mode ---
 constexpr int kScatterThreads = 256;
@@ -163,14 +87,6 @@ voxel_scatter_atomic_kernel(const double *__restrict__ ev, const int64_t *__rest
 }
 
 // ----------------------------------------- atomic mode, cluster (smem) path ---
-struct alignas(16) Partial {
-    double sum, sumsq;
-    long long nnz;
-    float mn, mx;
-};
-
-__device__ __forceinline__ float hot_filter(float v, float thr) { return (thr > 0.f && fabsf(v) > thr) ? 0.f : v; }
-
 // fp32 add into the shared memory of CTA `rank` of this cluster (DSMEM), no return value
 __device__ __forceinline__ void red_add_cluster(float *local_ptr, unsigned rank, float v) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(local_ptr);
@@ -526,36 +442,48 @@ det_accumulate_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restr
 
 // ---------------------------------------------- statistics + normalisation ---
 constexpr int kStatThreads = 256;
-constexpr int kMaxChunks = 256;
 
+// Both kernels: one CTA = one chunk of a window; a thread streams its float4s with 4 loads in flight.
+// (Round-1a sized them for 296 CTAs with one load in flight per thread: 43 of 70 us at 8 x 480x640.)
 __global__ void __launch_bounds__(kStatThreads)
 voxel_stats_kernel(const float *__restrict__ grid, int64_t cells, int64_t chunk_len, float hot_thr,
                    Partial *__restrict__ partials, int chunks) {
     const int b = blockIdx.y, c = blockIdx.x;
     const float *g = grid + (int64_t)b * cells;
     const int64_t s = (int64_t)c * chunk_len, e = min(cells, s + chunk_len);
-    double sum = 0.0, sumsq = 0.0;
-    long long nnz = 0;
+    // short fp32 partials per thread (a few dozen terms), promoted to fp64 across threads and chunks
+    float fs = 0.f, fq = 0.f;
+    int fn = 0;
     float mn = INFINITY, mx = -INFINITY;
     auto take = [&](float raw) {
         const float v = hot_filter(raw, hot_thr);
-        sum += (double)v;
-        sumsq += (double)v * (double)v;
-        nnz += (v != 0.f);
+        fs += v;
+        fq = fmaf(v, v, fq);
+        fn += (v != 0.f);
         mn = fminf(mn, v);
         mx = fmaxf(mx, v);
     };
     if (((cells | chunk_len) & 3) == 0) {  // 128-bit loads (chunk starts stay 16-byte aligned)
         const float4 *g4 = reinterpret_cast<const float4 *>(g);
-        for (int64_t i = (s >> 2) + threadIdx.x; i < (e >> 2); i += kStatThreads) {
-            const float4 q = __ldg(g4 + i);
-            take(q.x); take(q.y); take(q.z); take(q.w);
+        const int64_t e4 = e >> 2;
+        for (int64_t i = (s >> 2) + threadIdx.x; i < e4; i += 4 * kStatThreads) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t j = i + (int64_t)u * kStatThreads;
+                q[u] = j < e4 ? __ldg(g4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i + (int64_t)u * kStatThreads < e4) { take(q[u].x); take(q[u].y); take(q[u].z); take(q[u].w); }
+            }
         }
     } else {
         for (int64_t i = s + threadIdx.x; i < e; i += kStatThreads) take(__ldg(g + i));
     }
     // fixed-shape tree: deterministic for a given launch geometry
-    sum = warp_sum(sum); sumsq = warp_sum(sumsq); nnz = warp_sum(nnz);
+    double sum = warp_sum((double)fs), sumsq = warp_sum((double)fq);
+    long long nnz = warp_sum((long long)fn);
     mn = warp_min(mn); mx = warp_max(mx);
     __shared__ Partial sh[kStatThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -575,7 +503,23 @@ __global__ void __launch_bounds__(kStatThreads)
 voxel_normalise_kernel(const float *in, float *out /* may alias in */, int64_t cells, int64_t chunk_len,
                        float hot_thr, int mode, const Partial *__restrict__ partials, int chunks) {
     const int b = blockIdx.y, c = blockIdx.x;
-    __shared__ double s_a, s_b;   // out = (v - s_a) * s_b
+    const float *g = in + (int64_t)b * cells;
+    float *o = out + (int64_t)b * cells;
+    const int64_t s = (int64_t)c * chunk_len, e = min(cells, s + chunk_len);
+    const bool vec = ((cells | chunk_len) & 3) == 0;
+    // this thread's first loads go out before the window's partials are reduced
+    const float4 *g4 = reinterpret_cast<const float4 *>(g);
+    float4 *o4 = reinterpret_cast<float4 *>(o);
+    const int64_t e4 = e >> 2, i0 = (s >> 2) + threadIdx.x;
+    float4 q[4];
+    if (vec) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t j = i0 + (int64_t)u * kStatThreads;
+            q[u] = j < e4 ? g4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __shared__ float s_a, s_b;   // out = (v - s_a) * s_b
     __shared__ int s_identity;
     if (threadIdx.x < 32) {
         // every CTA of a window re-reduces the window's partials in the same fixed order
@@ -594,35 +538,40 @@ voxel_normalise_kernel(const float *in, float *out /* may alias in */, int64_t c
                 s_identity = nnz == 0;  // event_process.py:205 -- untouched when there is no non-zero entry
                 const double mean = nnz ? sum / (double)nnz : 0.0;
                 const double var = nnz ? sumsq / (double)nnz - mean * mean : 0.0;
-                s_a = mean;
-                s_b = 1.0 / (sqrt(fmax(var, 0.0)) + 1e-8);
+                s_a = (float)mean;
+                s_b = (float)(1.0 / (sqrt(fmax(var, 0.0)) + 1e-8));
             } else {
                 s_identity = 0;
-                s_a = (double)mn;
-                s_b = 1.0 / ((double)mx - (double)mn + 1e-8);
+                s_a = mn;
+                s_b = (float)(1.0 / ((double)mx - (double)mn + 1e-8));
             }
         }
     }
     __syncthreads();
-    const double a = s_a, inv = s_b;
+    const float a = s_a, inv = s_b;
     const bool identity = s_identity != 0;
-    const float *g = in + (int64_t)b * cells;
-    float *o = out + (int64_t)b * cells;
-    const int64_t s = (int64_t)c * chunk_len, e = min(cells, s + chunk_len);
-    // one fp64 subtract + multiply per NON-ZERO cell (a true fp64 divide per cell made this
-    // kernel 3x slower than the scatter itself); the result is rounded once to fp32
+    // mean and 1/(std+eps) are formed in fp64 once per window; the per-cell map is fp32 (1 ulp of the
+    // fp64 formula rounded to fp32; a true fp64 divide per cell made this kernel 3x slower than the scatter)
     auto norm = [&](float raw) -> float {
         const float v = hot_filter(raw, hot_thr);
         if (identity) return v;
-        if (mode == CF_PRE_STD) return (v != 0.f) ? (float)(((double)v - a) * inv) : 0.f;
-        return (float)(((double)v - a) * inv);
+        const float r = (v - a) * inv;
+        return (mode == CF_PRE_STD && v == 0.f) ? 0.f : r;
     };
-    if (((cells | chunk_len) & 3) == 0) {
-        const float4 *g4 = reinterpret_cast<const float4 *>(g);
-        float4 *o4 = reinterpret_cast<float4 *>(o);
-        for (int64_t i = (s >> 2) + threadIdx.x; i < (e >> 2); i += kStatThreads) {
-            const float4 q = g4[i];
-            o4[i] = make_float4(norm(q.x), norm(q.y), norm(q.z), norm(q.w));
+    if (vec) {
+        for (int64_t i = i0; i < e4; i += 4 * kStatThreads) {
+            if (i != i0) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t j = i + (int64_t)u * kStatThreads;
+                    q[u] = j < e4 ? g4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t j = i + (int64_t)u * kStatThreads;
+                if (j < e4) o4[j] = make_float4(norm(q[u].x), norm(q[u].y), norm(q[u].z), norm(q[u].w));
+            }
         }
     } else {
         for (int64_t i = s + threadIdx.x; i < e; i += kStatThreads) o[i] = norm(g[i]);
@@ -630,9 +579,9 @@ voxel_normalise_kernel(const float *in, float *out /* may alias in */, int64_t c
 }
 
 static void stat_geometry(int B, int64_t cells, int &chunks, int64_t &chunk_len) {
-    // enough CTAs to fill 148 SMs twice, chunks of >= 4096 cells, <= kMaxChunks per window
-    int64_t want = ceil_div(2 * 148, B > 0 ? B : 1);
-    int64_t cap = ceil_div(cells, 4096);
+    // ~8 CTAs per SM over the batch, chunks of >= 2048 cells (2 float4 per thread), <= kMaxChunks per window
+    int64_t want = ceil_div(8 * 148, B > 0 ? B : 1);
+    int64_t cap = ceil_div(cells, 2048);
     chunks = (int)(want < 1 ? 1 : want);
     if (chunks > cap) chunks = (int)(cap < 1 ? 1 : cap);
     if (chunks > kMaxChunks) chunks = kMaxChunks;
@@ -658,7 +607,35 @@ static int run_preprocess(const float *in, float *out, int B, int64_t cells, int
     return CF_OK;
 }
 
-// CF_VOXEL_FLAGS (debug / experiments): bit1 = use the cluster / DSMEM-atomics path, bit0 = do not chunk
+// implemented in voxel_tiled.cu (the default ATOMIC path)
+size_t voxel_tiled_workspace_bytes(int64_t total, int B, int nb, int H, int W, int flavour);
+int launch_voxel_tiled(const double *events, const int64_t *offsets, int64_t total, int B, int nb, int H, int W,
+                       int flavour, int preprocess, float hot_thr, float *out, void *ws, size_t ws_bytes,
+                       cudaStream_t stream);
+
+// ATOMIC mode has two data paths with identical numerics (sum order unspecified in both):
+//   L2 atomics (this file, the default): zero -> RED.ADD into the L2-resident grid -> statistics ->
+//     normalise in place;
+//   tiled (voxel_tiled.cu, CF_VOXEL_ATOMIC_TILED): partition into 12-byte records -> accumulate tiles in
+//     shared memory -> statistics, normalisation and the only write of the grid out of shared memory.
+// Measured on the B200 (scripts/scale_bench.py, us per launch, fused std normalisation, round 1):
+//                 8x180x240  64x180x240  1x260x346  64x260x346  8x480x640  1x624x970
+//   L2 atomics       16.4       50.8       10.3       132.0       43.8       30.0
+//   tiled            19.4      107.5       15.4       160.1       57.1       49.6
+// The tiled path issues no global atomic, but its two kernels are each a chain of dependent steps
+// (window lookup -> event loads -> fp64 decode -> counting sort -> write; run bounds -> records ->
+// shared-memory atomics -> statistics -> per-window barrier -> normalise -> write: timelines from
+// scripts/voxel_trace.py in profiles/), two waves are needed as soon as the batch's grids exceed the
+// chip's 33 MB of shared memory, and the ~100 G/s of L2 atomics it avoids were not the bound once the
+// statistics/normalise kernels were given enough loads in flight.  So the L2 path is the default and the
+// tiled path stays selectable (and tested) for the next round's work on it.
+static int voxel_flags();
+static bool use_tiled(int64_t, int, int64_t) {
+    return (voxel_flags() & 8) != 0;              // experiments: CF_VOXEL_FLAGS=8 forces the tiled path
+}
+
+// CF_VOXEL_FLAGS (debug / experiments): bit3 = force the tiled path, bit2 = force the L2-atomic path, bit1 = use the cluster / DSMEM-atomics
+// path, bit0 = do not chunk
 static int voxel_flags() {
     static int flags = -1;
     if (flags < 0) {
@@ -748,9 +725,11 @@ extern "C" size_t cf_preprocess_workspace_bytes(int B, int64_t) {
     return (size_t)(B > 0 ? B : 1) * cf::kMaxChunks * sizeof(cf::Partial);
 }
 
-extern "C" size_t cf_voxel_workspace_bytes(int64_t total_events, int B, int, int, int, int mode, int, int) {
+extern "C" size_t cf_voxel_workspace_bytes(int64_t total_events, int B, int nb, int H, int W, int mode, int flavour, int) {
     size_t base = cf::align_up(cf_preprocess_workspace_bytes(B, 0), 256);
     if (mode == CF_VOXEL_DETERMINISTIC) return cf::det_layout(total_events, base).end;
+    if (mode != CF_VOXEL_ATOMIC_L2 && nb > 0 && H > 0 && W > 0)
+        base += cf::voxel_tiled_workspace_bytes(total_events, B, nb, H, W, flavour);
     return base;
 }
 
@@ -775,7 +754,9 @@ extern "C" int cf_voxel_bin(const double *events, const int64_t *offsets, int64_
     CF_REQUIRE(total == 0 || events, CF_ERR_NULL, "cf_voxel_bin: events is null");
     CF_REQUIRE(nb > 0 && H > 0 && W > 0, CF_ERR_INVALID_ARG, "cf_voxel_bin: num_bins, width, height must be > 0");
     CF_REQUIRE(B >= 0 && total >= 0, CF_ERR_INVALID_ARG, "cf_voxel_bin: negative size");
-    CF_REQUIRE(mode == CF_VOXEL_ATOMIC || mode == CF_VOXEL_DETERMINISTIC, CF_ERR_INVALID_ARG, "cf_voxel_bin: bad mode %d", mode);
+    CF_REQUIRE(mode >= CF_VOXEL_ATOMIC && mode <= CF_VOXEL_ATOMIC_TILED, CF_ERR_INVALID_ARG, "cf_voxel_bin: bad mode %d", mode);
+    const bool force_l2 = mode == CF_VOXEL_ATOMIC_L2, force_tiled = mode == CF_VOXEL_ATOMIC_TILED;
+    if (force_l2 || force_tiled) mode = CF_VOXEL_ATOMIC;
     CF_REQUIRE(flavour >= CF_FLAVOUR_TORCH && flavour <= CF_FLAVOUR_POL, CF_ERR_INVALID_ARG, "cf_voxel_bin: bad flavour %d", flavour);
     CF_REQUIRE(preprocess >= CF_PRE_NONE && preprocess <= CF_PRE_MAXMIN, CF_ERR_INVALID_ARG, "cf_voxel_bin: bad preprocess %d", preprocess);
     CF_REQUIRE(total == 0 || aligned16(events), CF_ERR_ALIGN, "cf_voxel_bin: events not 16-byte aligned");
@@ -788,12 +769,26 @@ extern "C" int cf_voxel_bin(const double *events, const int64_t *offsets, int64_
         int rc = launch_cluster_path(events, offsets, B, nb, H, W, flavour, preprocess, hot_thr, out, cells, stream);
         if (rc != 1) return rc;  // 1 = grid too large for the cluster path -> global path below
     }
+    if (mode == CF_VOXEL_ATOMIC && !force_l2 && !(voxel_flags() & 4) &&
+        (force_tiled || use_tiled(total, B, (int64_t)nb * planes * H * W))) {
+        const size_t base = align_up(cf_preprocess_workspace_bytes(B, 0), 256);
+        const size_t need = voxel_tiled_workspace_bytes(total, B, nb, H, W, flavour);
+        if (need > 0 && total > 0) {
+            CF_REQUIRE(ws && ws_bytes >= base + need, CF_ERR_WORKSPACE, "cf_voxel_bin: workspace too small (%zu < %zu)",
+                       ws_bytes, base + need);
+            const int rc = launch_voxel_tiled(events, offsets, total, B, nb, H, W, flavour, preprocess, hot_thr, out,
+                                              reinterpret_cast<char *>(ws) + base, ws_bytes - base, stream);
+            if (rc != 1) return rc;  // 1 = geometry not covered -> L2-atomic path below
+        }
+        CF_REQUIRE(!force_tiled || total == 0, CF_ERR_UNSUPPORTED,
+                   "cf_voxel_bin: CF_VOXEL_ATOMIC_TILED does not cover B=%d, %dx%d, nb=%d", B, H, W, nb);
+    }
     if (mode == CF_VOXEL_ATOMIC) {
         // Chunks of windows that stay L2-resident from the zero-fill to the normalised write-back.
         // The host does not know the per-window event counts (offsets live on the device), so the
         // events of a chunk are budgeted with the batch average; kernels take device offsets.
         const size_t per_window = (size_t)cells * sizeof(float) + (size_t)(total / B + 1) * 32;
-        int chunk = (voxel_flags() & 1) ? B : (int)((48ull << 20) / per_window);
+        int chunk = (voxel_flags() & 1) ? B : (int)((96ull << 20) / per_window);
         if (chunk < 1) chunk = 1;
         if (chunk > B) chunk = B;
         if (preprocess != CF_PRE_NONE) {

@@ -40,7 +40,10 @@ from . import _lib
 # sequential accumulation).  Override per call with mode=... or globally here.
 DEFAULT_MODE = os.environ.get("CISTAFLOW_VOXEL_MODE", "atomic")
 
-_MODES = {"atomic": _lib.VOXEL_ATOMIC, "deterministic": _lib.VOXEL_DETERMINISTIC}
+_MODES = {"atomic": _lib.VOXEL_ATOMIC, "deterministic": _lib.VOXEL_DETERMINISTIC,
+          # 'atomic' with the data path forced (tests / experiments): RED.ADD into the L2-resident grid, or
+          # partition + shared-memory tiles (no global atomics)
+          "atomic_l2": _lib.VOXEL_ATOMIC_L2, "atomic_tiled": _lib.VOXEL_ATOMIC_TILED}
 _PRE = {None: _lib.PRE_NONE, "none": _lib.PRE_NONE, "std": _lib.PRE_STD, "maxmin": _lib.PRE_MAXMIN}
 _FLAVOURS = {"torch": _lib.FLAVOUR_TORCH, "numpy": _lib.FLAVOUR_NUMPY, "pol": _lib.FLAVOUR_POL}
 

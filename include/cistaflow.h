@@ -72,8 +72,12 @@ CF_API const char *cf_last_kernel(void);
  *           utils/event_process.py:193-239  event_preprocess(_pytorch)   (preprocess != NONE)
  * ------------------------------------------------------------------------- */
 typedef enum cf_voxel_mode {
-    CF_VOXEL_ATOMIC = 0,       /* fast: fp32 atomics, sum order unspecified (<= 1e-5 rel.)   */
-    CF_VOXEL_DETERMINISTIC = 1 /* bit-exact: per-cell sums in the reference's event order    */
+    CF_VOXEL_ATOMIC = 0,        /* fast: fp32 atomics, sum order unspecified (<= 1e-5 rel.);  */
+                                /* the library picks the data path (L2 or tiled) by size      */
+    CF_VOXEL_DETERMINISTIC = 1, /* bit-exact: per-cell sums in the reference's event order    */
+    CF_VOXEL_ATOMIC_L2 = 2,     /* ATOMIC, forced path: RED.ADD into the L2-resident grid     */
+    CF_VOXEL_ATOMIC_TILED = 3   /* ATOMIC, forced path: partition + shared-memory tiles;      */
+                                /* CF_ERR_UNSUPPORTED when the geometry does not fit          */
 } cf_voxel_mode;
 
 typedef enum cf_voxel_flavour {

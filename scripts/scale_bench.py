@@ -105,10 +105,11 @@ def main():
                     ev, off = tile_windows(ev, off, B)
                     sets.append((torch.from_numpy(ev).to(dev), torch.from_numpy(off).to(dev),
                                  torch.empty((B, 5, H, W), device=dev)))
-                for label, norm in (("voxel+norm", "std"), ("voxel_only", None)):
+                for label, norm, path in (("voxel+norm", "std", "atomic"), ("voxel+norm[l2]", "std", "atomic_l2"),
+                                          ("voxel+norm[tiled]", "std", "atomic_tiled"), ("voxel_only", None, "atomic")):
                     fns = [(lambda e=e, o=o, out=out: cf.events_to_voxel_grid_batched(
                         e, o, 5, W, H, normalize=norm, filter_hot_pixel=norm is not None, flavour="numpy",
-                        mode="atomic", out=out)) for (e, o, out) in sets]
+                        mode=path, out=out)) for (e, o, out) in sets]
                     t = graph_time(fns, stream, inner=2 * ns)
                     row[label] = {"us": t * 1e6, "GB/s": nbytes / t / 1e9, "frac_hbm": nbytes / t / 1e9 / hbm,
                                   "Mev/s": B * nev / t / 1e6, "bytes": nbytes}
