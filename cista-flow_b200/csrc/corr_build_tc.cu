@@ -74,6 +74,10 @@ struct Params {
     int h1, w1;    // level-1 map size
     float scale;
     int stream_l0; // 1: level 0 is larger than L2 can hold -> evict-first stores
+    int b3d;       // as atoms3d, for the B operand: also needs tile origins on atom boundaries (BN % 32 == 0)
+    int atoms3d;   // 1: N % 32 == 0 -> the tensor maps are 3-D {32 cols, rows, 32-column atoms}: ONE TMA instruction
+                   //    per operand and stage.  One thread issues a cp.async.bulk.tensor about every 100 cycles, and
+                   //    9-12 per-atom boxes per stage made that issue rate the bound of the main loop (timeline)
     float *l0;
     float *l1;
 };
@@ -118,6 +122,13 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, int
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 
@@ -169,10 +180,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, MN-major, 128B swizzle with 32B atoms (see file header)
-__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo = 4096u) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address            bits [0,14)
-    d |= (uint64_t)(4096u >> 4) << 16;               // leading byte offset (MN) bits [16,30)
+    d |= (uint64_t)(lbo >> 4) << 16;                 // leading byte offset (MN) bits [16,30): bytes per TMA box
     d |= (uint64_t)(512u >> 4) << 32;                // stride byte offset (K)   bits [32,46)
     d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
     d |= (uint64_t)1 << 61;                          // layout type 1 = SWIZZLE_128B_BASE32B
@@ -275,9 +286,17 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + A_BYTES;
                     mbar_expect_tx(&full[stage], tx_bytes);
                     const int krow = b * p.D + kb * BK;
+                    if (p.atoms3d) {
+                        tma_load_3d(sa, &tmap_a, 0, krow, i0 >> 5, &full[stage]);
+                    } else {
 #pragma unroll
-                    for (int a = 0; a < BM / 32; ++a) tma_load_2d(sa + a * BOX_BYTES, &tmap_a, i0 + 32 * a, krow, &full[stage]);
-                    for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOX_BYTES, &tmap_b, j0 + 32 * a, krow, &full[stage]);
+                        for (int a = 0; a < BM / 32; ++a) tma_load_2d(sa + a * BOX_BYTES, &tmap_a, i0 + 32 * a, krow, &full[stage]);
+                    }
+                    if (p.b3d) {
+                        tma_load_3d(sb, &tmap_b, 0, krow, j0 >> 5, &full[stage]);
+                    } else {
+                        for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOX_BYTES, &tmap_b, j0 + 32 * a, krow, &full[stage]);
+                    }
                     if (tile == (int)blockIdx.x && kb == 0) stamp(2);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -421,6 +440,18 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (threadIdx.x == 0) stamp(22);
 }
 
+// ---- measured and dropped: A-resident variant --------------------------------------------------
+// Round 1 also built a variant that keeps the 128 x D slice of fmap1 resident in shared memory (128 KB)
+// for a whole range of target tiles, streaming only fmap2 (operand traffic per 128x160 tile 160 KB
+// instead of 288 KB).  It was SLOWER (8 x 60x80: 426 us against 327 us; 1 x 80x124: 248 against 198):
+// with 128 KB pinned only ~64 KB are left for the fmap2 ring, and at ~1.6 us of loaded TMA latency
+// 60 KB in flight sustain ~37 KB/us per SM -- the streaming kernel keeps 144 KB in flight.  The per-tile
+// timeline (scripts/corr_trace.py at that commit) showed the main loop waiting on loads, the epilogue
+// (3.4-3.9 us per tile) hidden behind it.  What did help both variants: ONE 3-D TMA instruction per
+// operand and stage (atoms3d / b3d above) instead of 9-12 per-atom boxes -- a single thread issues a
+// cp.async.bulk.tensor only about every 100 cycles, which was the main-loop bound (368 -> 327 us).
+// Next lever (not done): cta_group::2 pairs (M = 256 across two SMs, each loading half of the fmap2 tile).
+
 // ---- host side --------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -439,16 +470,32 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D map over a feature map viewed as [B*D rows, N cols], box 32 x 32, 128B swizzle / 32B atoms
-static int make_fmap_tmap(CUtensorMap *m, const float *base, int B, int D, int N, CUtensorMapDataType dt) {
+static int make_fmap_tmap(CUtensorMap *m, const float *base, int B, int D, int N, CUtensorMapDataType dt, int box_rows = 32) {
     EncodeTiledFn fn = encode_fn();
     CF_REQUIRE(fn, CF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)B * D};
     cuuint64_t strides[1] = {(cuuint64_t)N * sizeof(float)};
-    cuuint32_t box[2] = {32, 32};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, dt, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return CF_OK;
+}
+
+// The same feature map as a 3-D tensor {32 cols, B*D rows, N/32 column atoms} (N % 32 == 0): a box
+// {32, rows, atoms} lands in shared memory as [atom][row][32 cols] -- the UMMA MN-major layout -- in ONE instruction
+static int make_fmap_tmap3(CUtensorMap *m, const float *base, int B, int D, int N, CUtensorMapDataType dt, int box_rows,
+                           int box_atoms) {
+    EncodeTiledFn fn = encode_fn();
+    CF_REQUIRE(fn, CF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {32, (cuuint64_t)B * D, (cuuint64_t)N / 32};
+    cuuint64_t strides[2] = {(cuuint64_t)N * sizeof(float), 128};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_atoms};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, dt, 3, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_CUDA, "cuTensorMapEncodeTiled (3-D feature map) failed with CUresult %d", (int)r);
     return CF_OK;
 }
 
@@ -475,7 +522,7 @@ bool corr_tensor_core_supported(int D, int h, int w) {
 size_t corr_tc_workspace_bytes(int, int, int, int) { return 0; }
 
 // flags (debug/experiments, env CF_TC_FLAGS): bit1 = encode the tensor maps as plain FLOAT32 (operands are
-// then truncated, not rounded, to TF32), bit2 = never fuse the pooling.
+// then truncated, not rounded, to TF32), bit2 = never fuse the pooling, bit4 = per-atom 2-D TMA boxes even when N % 32 == 0.
 int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int h, int w, float scale, float *level0,
                             float *level1, int precision, void *, size_t, int flags, int *fused_level1,
                             cudaStream_t stream) {
@@ -514,9 +561,19 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     p.total_tiles = (int)total;
 
     const CUtensorMapDataType dt = (flags & 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+    p.atoms3d = (N % 32 == 0) && !(flags & 16);
+    p.b3d = p.atoms3d && (p.BN % 32 == 0 || p.tiles_n == 1);
     CUtensorMap ta, tb, tcm;
-    if (int rc = make_fmap_tmap(&ta, a, B, D, N, dt)) return rc;
-    if (int rc = make_fmap_tmap(&tb, bm, B, D, N, dt)) return rc;
+    if (p.atoms3d) {
+        if (int rc = make_fmap_tmap3(&ta, a, B, D, N, dt, BK, BM / 32)) return rc;
+    } else {
+        if (int rc = make_fmap_tmap(&ta, a, B, D, N, dt)) return rc;
+    }
+    if (p.b3d) {
+        if (int rc = make_fmap_tmap3(&tb, bm, B, D, N, dt, BK, p.n_boxes_b)) return rc;
+    } else {
+        if (int rc = make_fmap_tmap(&tb, bm, B, D, N, dt)) return rc;
+    }
     if (int rc = make_volume_tmap(&tcm, level0, B, N)) return rc;
 
     int dev = 0;
@@ -526,7 +583,8 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         opt_in[dev & 63] = true;
     }
-    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    const int sms = sm_count();
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     corr_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, tcm, p);
     CF_LAUNCH_CHECK("corr_tc_kernel");
     return CF_OK;

@@ -371,7 +371,7 @@ def test_lookup_on_reference_pyramid(golden, cuda_device):
     assert np.abs(out.cpu().numpy()[0, :, 0, 0]).max() == 0.0  # query far outside: zero padding everywhere
 
 
-@pytest.mark.parametrize("h,w,batch", [(180, 240, 8), (260, 346, 1), (480, 640, 1)])
+@pytest.mark.parametrize("h,w,batch", [(180, 240, 8), (260, 346, 1), (480, 640, 1), (624, 970, 1), (128, 192, 2)])
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
 def test_corr_vs_oracle_config_shapes(cuda_device, h, w, batch, precision, tol):
     f1, f2, coords = synth.corr_inputs(batch, h, w, seed=9)
