@@ -37,8 +37,13 @@ import subprocess
 import sys
 import time
 
-import numpy as np
-import torch
+# torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 also times the CPU reference arm, which must get all
+# host cores (the in-run CPU baseline of a 2-GPU run was 40x slower than the stand-alone one before this)
+if os.environ.get("OMP_NUM_THREADS") == "1" and os.environ.get("RANK", "0") == "0":
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -123,6 +128,25 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes of one launch of `kernel_prefix` from the committed ncu summary (None when absent)."""
+    path = os.path.join(ROOT, "profiles", "r01", "step_kernels_ncu_full.txt")
+    try:
+        lines = open(path).read().splitlines()
+    except OSError:
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for i, line in enumerate(lines):
+        if line.startswith("---") and kernel_prefix in line:
+            tot = 0.0
+            for l2 in lines[i + 1:i + 8]:
+                parts = l2.split()
+                if parts and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(parts[1]) * unit.get(parts[2], 1.0)
+            return tot
+    return None
 
 
 # ---- CPU reference arm ------------------------------------------------------------------
@@ -359,6 +383,22 @@ def run_ours(args, cfg):
         t_warp = graph_time(lambda d: cf.warp_frame_and_codes(d["img"], d["codes"], d["flow"], cfg["warp_mode"]), inner=4)
         t_build = graph_time(lambda d: cf.build_pyramid(d["fmap1"], d["fmap2"], cfg["levels"]), inner=4)
 
+    # -- the same four kernels at the larger BASELINE shapes (rank 0 of a 1-GPU run only; ~10 s): at configs[1]
+    #    every kernel runs 7-30 us and launch ramp / dependent-latency chains decide the fraction; these rows show
+    #    where each kernel sits once the launch is long enough to be bandwidth- or tensor-bound
+    at_scale = None
+    if world == 1 and not args.no_scale:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("scale_bench", os.path.join(ROOT, "scripts", "scale_bench.py"))
+        sb = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(sb)
+        rows_, _ = sb.run_cases(["cfg2_180x240_b64", "cfg5_480x640_b8", "cfg4_624x970_b1"],
+                                {"voxel", "warp", "build", "lookup"}, dev=dev, verbose=False, voxel_paths=False)
+        at_scale = {}
+        for r_ in rows_:
+            at_scale[r_["case"]] = {k: {kk: vv for kk, vv in v.items() if kk in ("us", "GB/s", "frac_hbm", "TF/s_tf32", "frac_tf32", "Mev/s")}
+                                    for k, v in r_.items() if isinstance(v, dict)}
+
     # -- reduce over ranks (max), gather the per-rank table (the only collective)
     step_ms = sharding.max_over_ranks(dev_ms / args.steps, dev)
     e2e_step_ms = sharding.max_over_ranks(e2e_ms / e2e_steps, dev)
@@ -402,7 +442,10 @@ def run_ours(args, cfg):
     }
     share = {k: v["ms_per_launch"] * (cfg["lookups"] if k == "corr_lookup" else 1) for k, v in kernels.items()}
     roof = dict(kernels["corr_lookup"])
-    roof.update({"kernel": "corr_lookup_kernel<4>", "traffic": None, "peak_source": peak_src,
+    roof.update({"kernel": "corr_lookup_kernel<4>", "traffic": ncu_traffic("corr_lookup_kernel"), "peak_source": peak_src,
+                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full "
+                                 "capture (profiles/r01/step_kernels_ncu_full.txt); the 8 MB output of a single replayed "
+                                 "launch stays in the 126 MB L2, so the write-back is not inside the kernel's window",
                  "share_of_step": share["corr_lookup"] / sum(share.values()),
                  "note": "timed alone: 12 launches per CUDA-graph replay, CUDA events on the launching stream"})
 
@@ -428,6 +471,7 @@ def run_ours(args, cfg):
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roof,
         "kernels": kernels,
+        "kernels_at_scale": at_scale,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "per_rank_ms": {"step": table[:, 0].tolist(), "e2e_step": table[:, 1].tolist()},
@@ -441,6 +485,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-scale", action="store_true", help="skip the per-kernel timings at the larger BASELINE shapes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = dict(CFG)

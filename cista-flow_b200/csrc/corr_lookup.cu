@@ -57,6 +57,7 @@ corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict_
     const int b = blockIdx.y;
     const int q0 = blockIdx.x * QT;
     const float *cb = coords + (size_t)b * 2 * N;
+    if (tid == 0) CF_TRACE_AT(0);
     if (tid < QT) {
         const int q = q0 + tid;
         // clamp keeps (int) conversions defined for wild coordinates; anything
@@ -134,7 +135,9 @@ corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict_
             patch[qi * PS + e] = v;
         }
     }
+    if (tid == 0) CF_TRACE_AT(1);
     __syncthreads();
+    if (tid == 0) CF_TRACE_AT(2);
 
     // ---- phase B: bilinear samples, coalesced channel-major stores ---------------
     constexpr int CPW = 32 / QT;                      // channels per warp-iteration
@@ -199,7 +202,10 @@ corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict_
             }
         }
     }
+    if (tid == 0) CF_TRACE_AT(3);
 }
+
+CF_DEFINE_TRACE_SETTER(cf_trace_buffer_lookup)
 
 template <int RADIUS, int LEVELS, int QT>
 static int launch_lookup(const Pyramid &pyr, const float *coords, float *out, int B, int N, int levels, int radius,

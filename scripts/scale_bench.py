@@ -75,20 +75,16 @@ def tile_windows(ev, off, B):
     return evs[:offs[-1]], offs
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "scale_bench.json"))
-    ap.add_argument("--only", default="voxel,warp,build,lookup")
-    ap.add_argument("--cases", default=",".join(CASES))
-    args = ap.parse_args()
-    only = set(args.only.split(","))
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
+def run_cases(cases, only, dev=None, verbose=True, voxel_paths=True):
+    """Times the kernels named in `only` at the shapes named in `cases`; returns (rows, peaks)."""
+    if dev is None:
+        dev = torch.device("cuda", 0)
+        torch.cuda.set_device(dev)
     stream = torch.cuda.Stream(dev)
     hbm, tf32, src = peaks()
     rows = []
     with torch.cuda.stream(stream):
-        for name in args.cases.split(","):
+        for name in cases:
             H, W, B, nev = CASES[name]
             hp, wp = synth.padded_dims(H, W)
             h, w = hp // 8, wp // 8
@@ -105,8 +101,9 @@ def main():
                     ev, off = tile_windows(ev, off, B)
                     sets.append((torch.from_numpy(ev).to(dev), torch.from_numpy(off).to(dev),
                                  torch.empty((B, 5, H, W), device=dev)))
-                for label, norm, path in (("voxel+norm", "std", "atomic"), ("voxel+norm[l2]", "std", "atomic_l2"),
-                                          ("voxel+norm[tiled]", "std", "atomic_tiled"), ("voxel_only", None, "atomic")):
+                variants = (("voxel+norm", "std", "atomic"), ("voxel+norm[l2]", "std", "atomic_l2"),
+                            ("voxel+norm[tiled]", "std", "atomic_tiled"), ("voxel_only", None, "atomic"))
+                for label, norm, path in (variants if voxel_paths else variants[:1]):
                     fns = [(lambda e=e, o=o, out=out: cf.events_to_voxel_grid_batched(
                         e, o, 5, W, H, normalize=norm, filter_hot_pixel=norm is not None, flavour="numpy",
                         mode=path, out=out)) for (e, o, out) in sets]
@@ -161,7 +158,19 @@ def main():
                 del sets
             torch.cuda.empty_cache()
             rows.append(row)
-            print(json.dumps(row), flush=True)
+            if verbose:
+                print(json.dumps(row), flush=True)
+    return rows, {"hbm_gbs": hbm, "tf32_tflops": tf32, "source": src}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "scale_bench.json"))
+    ap.add_argument("--only", default="voxel,warp,build,lookup")
+    ap.add_argument("--cases", default=",".join(CASES))
+    args = ap.parse_args()
+    rows, pk = run_cases(args.cases.split(","), set(args.only.split(",")))
+    hbm, tf32, src = pk["hbm_gbs"], pk["tf32_tflops"], pk["source"]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump({"peaks": {"hbm_gbs": hbm, "tf32_tflops": tf32, "source": src}, "rows": rows}, open(args.out, "w"), indent=1)
     print(f"\n{'case':20s} {'kernel':22s} {'us':>10s} {'GB/s':>9s} {'%HBM':>6s}  extra")
