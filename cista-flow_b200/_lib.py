@@ -37,8 +37,12 @@ SYMBOLS = {
     "cf_voxel_bin": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _sz, _vp]),
     "cf_preprocess_workspace_bytes": (_sz, [_i, _i64]),
     "cf_voxel_preprocess": (_i, [_vp, _vp, _i, _i64, _i, _f, _vp, _sz, _vp]),
+    "cf_events_pack": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "cf_voxel_bin_packed": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp, _vp, _sz, _vp]),
     "cf_warp": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "cf_warp_frame_and_codes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "cf_voxel_flow_warp_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cf_voxel_flow_warp": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cf_corr_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "cf_corr_build": (_i, [_vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _i, _vp, _sz, _vp]),
     "cf_corr_lookup": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _vp, _vp]),

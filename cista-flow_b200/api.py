@@ -2,17 +2,18 @@
 from ._lib import CistaFlowError, LIB_PATH, load as load_library
 from .corr import CorrBlock, build_pyramid, coords_grid, lookup as corr_lookup
 from .event_process import (event_preprocess, event_preprocess_batched, event_preprocess_pytorch,
-                            events_to_voxel_grid, events_to_voxel_grid_batched, events_to_voxel_grid_pol,
-                            events_to_voxel_grid_pytorch)
+                            events_to_voxel_grid, events_to_voxel_grid_batched, events_to_voxel_grid_packed,
+                            events_to_voxel_grid_pol, events_to_voxel_grid_pytorch, pack_events, pack_events_host)
 from .flow_utils import FrameWarp, backWarp, forwardWarp, warp, warp_frame_and_codes
 from .install import install, uninstall
+from .loss import voxel_warping_flow_loss
 
 __all__ = [
     "CistaFlowError", "LIB_PATH", "load_library",
     "CorrBlock", "build_pyramid", "coords_grid", "corr_lookup",
     "event_preprocess", "event_preprocess_batched", "event_preprocess_pytorch",
-    "events_to_voxel_grid", "events_to_voxel_grid_batched", "events_to_voxel_grid_pol",
-    "events_to_voxel_grid_pytorch",
+    "events_to_voxel_grid", "events_to_voxel_grid_batched", "events_to_voxel_grid_packed", "events_to_voxel_grid_pol",
+    "events_to_voxel_grid_pytorch", "pack_events", "pack_events_host",
     "FrameWarp", "backWarp", "forwardWarp", "warp", "warp_frame_and_codes",
-    "install", "uninstall",
+    "install", "uninstall", "voxel_warping_flow_loss",
 ]

@@ -607,7 +607,13 @@ static int run_preprocess(const float *in, float *out, int B, int64_t cells, int
     return CF_OK;
 }
 
-// implemented in voxel_tiled.cu (the default ATOMIC path)
+// statistics + normalisation for the packed-event path (voxel_packed.cu)
+int run_preprocess_shared(const float *in, float *out, int B, int64_t cells, int preprocess, float hot_thr, void *ws,
+                          size_t ws_bytes, cudaStream_t stream) {
+    return run_preprocess(in, out, B, cells, preprocess, hot_thr, ws, ws_bytes, stream);
+}
+
+// implemented in voxel_tiled.cu (CF_VOXEL_ATOMIC_TILED)
 size_t voxel_tiled_workspace_bytes(int64_t total, int B, int nb, int H, int W, int flavour);
 int launch_voxel_tiled(const double *events, const int64_t *offsets, int64_t total, int B, int nb, int H, int W,
                        int flavour, int preprocess, float hot_thr, float *out, void *ws, size_t ws_bytes,

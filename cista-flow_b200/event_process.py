@@ -108,6 +108,78 @@ def events_to_voxel_grid_batched(events: torch.Tensor, offsets: torch.Tensor, nu
     return out
 
 
+# ---- packed event ingest (8 bytes per event; include/cistaflow.h part 1b) ---------------------------------
+def pack_events_host(events: np.ndarray, offsets: np.ndarray | None = None) -> np.ndarray:
+    """NumPy packer for the host side of the ingest path: float64 [N,4] rows (t, x, y, p) -> uint64 [N],
+    low word = float32 (t - t_first_of_window) (fp64 subtraction first), high word = x | y << 16 | p << 31.
+    Pack on the host, upload 8 B/event instead of 32 B/event.  Same bits as the device packer
+    (``pack_events`` on a CUDA tensor)."""
+    ev = np.ascontiguousarray(events, dtype=np.float64)
+    assert ev.ndim == 2 and ev.shape[1] == 4
+    n = ev.shape[0]
+    if offsets is None:
+        offsets = np.array([0, n], dtype=np.int64)
+    offsets = np.asarray(offsets, dtype=np.int64)
+    t0 = np.zeros(n, dtype=np.float64)
+    for b in range(len(offsets) - 1):
+        if offsets[b + 1] > offsets[b]:
+            t0[offsets[b]:offsets[b + 1]] = ev[offsets[b], 0]
+    t_rel = (ev[:, 0] - t0).astype(np.float32).view(np.uint32).astype(np.uint64)
+    ok = (ev[:, 1] >= 0) & (ev[:, 1] < 65535) & (ev[:, 2] >= 0) & (ev[:, 2] < 32768)
+    x = np.where(ok, ev[:, 1], 65535).astype(np.uint64)      # truncation like the kernels' (int) conversion
+    y = np.where(ok, ev[:, 2], 0).astype(np.uint64)
+    p = (ev[:, 3] > 0).astype(np.uint64)
+    return t_rel | ((x | (y << np.uint64(16)) | (p << np.uint64(31))) << np.uint64(32))
+
+
+def pack_events(events: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    """Device packer: CUDA float64 [N,4] + int64 offsets [B+1] -> int64 [N] (the bits of the uint64 records)."""
+    _lib.require_cuda(events, "events")
+    _lib.require_cuda(offsets, "offsets")
+    assert events.dim() == 2 and events.shape[1] == 4
+    events = events.double().contiguous()
+    offsets = offsets.to(torch.int64).contiguous()
+    packed = torch.empty(events.shape[0], dtype=torch.int64, device=events.device)
+    lib = _lib.load()
+    with torch.cuda.device(events.device):
+        rc = lib.cf_events_pack(_lib.ptr(events) if events.shape[0] else None, offsets.data_ptr(), events.shape[0],
+                                offsets.numel() - 1, packed.data_ptr(), _lib.stream_ptr(events.device))
+    _lib.check(rc, "cf_events_pack")
+    return packed
+
+
+def events_to_voxel_grid_packed(packed: torch.Tensor, offsets: torch.Tensor, num_bins: int, width: int, height: int,
+                                normalize: str | None = None, filter_hot_pixel: bool = False,
+                                hot_threshold: float | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``events_to_voxel_grid_batched`` for packed events (int64/uint64 CUDA tensor [sum N_b]): reads 8 B per
+    event.  Atomic-mode numerics; polarity and the 25/nb hot-pixel default follow ``events_to_voxel_grid``."""
+    _lib.require_cuda(packed, "packed")
+    _lib.require_cuda(offsets, "offsets")
+    assert packed.dim() == 1 and packed.element_size() == 8
+    assert num_bins > 0 and width > 0 and height > 0
+    packed = packed.contiguous()
+    offsets = offsets.to(torch.int64).contiguous()
+    B = offsets.numel() - 1
+    thr = 0.0
+    if filter_hot_pixel:
+        thr = hot_threshold if hot_threshold is not None else 25.0 / num_bins
+    dev = packed.device
+    shape = (B, num_bins, height, width)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+    else:
+        assert out.shape == shape and out.dtype == torch.float32 and out.is_contiguous() and out.device == dev
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.cf_preprocess_workspace_bytes(B, num_bins * height * width) if normalize else 0
+        ws = _lib.workspace(ws_bytes, dev)
+        rc = lib.cf_voxel_bin_packed(_lib.ptr(packed) if packed.numel() else None, offsets.data_ptr(), packed.numel(), B,
+                                     num_bins, height, width, _PRE[normalize], thr, out.data_ptr(), _lib.ptr(ws), ws_bytes,
+                                     _lib.stream_ptr(dev))
+    _lib.check(rc, "cf_voxel_bin_packed")
+    return out
+
+
 def _single_window(events_dev: torch.Tensor, num_bins, width, height, flavour, mode, **kw) -> torch.Tensor:
     n = events_dev.shape[0]
     offsets = torch.tensor([0, n], dtype=torch.int64, device=events_dev.device)

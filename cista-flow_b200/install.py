@@ -9,6 +9,7 @@ therefore rebinds the names *in every reference module that imported them*:
   data_readers.train_data_loaders / data_readers.MVSEC / test_noeval (same names)
   utils.flow_utils           backWarp, forwardWarp, FrameWarp
   e2v.e2v_model, loss        FrameWarp
+  loss, test_wo_flow, test_mvsec   voxel_warping_flow_loss (part "fwl")
   ERAFT.corr, ERAFT.eraft    CorrBlock
   DCEIFlow.core.corr.raft_corr, DCEIFlow.DCEIFlow   CorrBlock
 
@@ -22,39 +23,44 @@ import importlib
 import sys
 
 from . import corr, event_process, flow_utils
+from . import loss as loss_mod
 
 _VOXEL = {name: getattr(event_process, name) for name in (
     "events_to_voxel_grid", "events_to_voxel_grid_pol", "events_to_voxel_grid_pytorch",
     "event_preprocess", "event_preprocess_pytorch")}
 _WARP = {name: getattr(flow_utils, name) for name in ("backWarp", "forwardWarp", "FrameWarp")}
 _CORR = {"CorrBlock": corr.CorrBlock}
+_FWL = {"voxel_warping_flow_loss": loss_mod.voxel_warping_flow_loss}
 
 # module -> symbols to rebind there (only names the module already has are touched)
 TARGETS = {
-    "utils.event_process": _VOXEL,
-    "data_readers.video_readers": _VOXEL,
-    "data_readers.train_data_loaders": _VOXEL,
-    "data_readers.MVSEC": _VOXEL,
-    "test_noeval": _VOXEL,
-    "utils.flow_utils": _WARP,
-    "e2v.e2v_model": _WARP,
-    "loss": _WARP,
-    "ERAFT.corr": _CORR,
-    "ERAFT.eraft": _CORR,
-    "DCEIFlow.core.corr.raft_corr": _CORR,
-    "DCEIFlow.DCEIFlow": _CORR,
+    "utils.event_process": (_VOXEL,),
+    "data_readers.video_readers": (_VOXEL,),
+    "data_readers.train_data_loaders": (_VOXEL,),
+    "data_readers.MVSEC": (_VOXEL,),
+    "test_noeval": (_VOXEL,),
+    "utils.flow_utils": (_WARP,),
+    "e2v.e2v_model": (_WARP,),
+    "loss": (_WARP, _FWL),
+    "test_wo_flow": (_FWL,),
+    "test_mvsec": (_FWL,),
+    "ERAFT.corr": (_CORR,),
+    "ERAFT.eraft": (_CORR,),
+    "DCEIFlow.core.corr.raft_corr": (_CORR,),
+    "DCEIFlow.DCEIFlow": (_CORR,),
 }
 
 _saved: dict[tuple[str, str], object] = {}
 
 
-def install(import_missing: bool = True, parts=("voxel", "warp", "corr")) -> list[str]:
+def install(import_missing: bool = True, parts=("voxel", "warp", "corr", "fwl")) -> list[str]:
     """Rebind; returns the list of ``module.symbol`` names that were replaced."""
-    groups = {"voxel": _VOXEL, "warp": _WARP, "corr": _CORR}
+    groups = {"voxel": _VOXEL, "warp": _WARP, "corr": _CORR, "fwl": _FWL}
     active = [groups[p] for p in parts]
     done = []
-    for modname, table in TARGETS.items():
-        if not any(table is a for a in active):
+    for modname, tables in TARGETS.items():
+        tables = [t for t in tables if any(t is a for a in active)]
+        if not tables:
             continue
         mod = sys.modules.get(modname)
         if mod is None and import_missing:
@@ -64,11 +70,12 @@ def install(import_missing: bool = True, parts=("voxel", "warp", "corr")) -> lis
                 continue
         if mod is None:
             continue
-        for name, ours in table.items():
-            if hasattr(mod, name) and getattr(mod, name) is not ours:
-                _saved.setdefault((modname, name), getattr(mod, name))
-                setattr(mod, name, ours)
-                done.append(f"{modname}.{name}")
+        for table in tables:
+            for name, ours in table.items():
+                if hasattr(mod, name) and getattr(mod, name) is not ours:
+                    _saved.setdefault((modname, name), getattr(mod, name))
+                    setattr(mod, name, ours)
+                    done.append(f"{modname}.{name}")
     return done
 
 

@@ -121,6 +121,22 @@ CF_API int cf_voxel_preprocess(const float *in, float *out, int B, int64_t cells
                         void *workspace, size_t workspace_bytes, cf_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
+ * Part 1b: packed event ingest -- 8 bytes per event
+ * narrows the fp64 rows of data_readers/event_readers.py:6-47 to
+ *   word 0  float32 t_rel = (float)(t - t_first_of_window)   (fp64 subtraction first)
+ *   word 1  uint32  x | y << 16 | p << 31                    (x < 65535, y < 32768)
+ * ------------------------------------------------------------------------- */
+/* events float64 [total,4] + offsets int64 [B+1] (as cf_voxel_bin) -> packed uint64 [total]. */
+CF_API int cf_events_pack(const double *events, const int64_t *offsets, int64_t total_events, int B,
+                   void *packed, cf_stream_t stream);
+/* Voxel grid [B, nb, H, W] (+ fused event_preprocess) from packed events; ATOMIC numerics
+ * (|err| <= 1e-5 * (sum|w| + 1) per cell against the fp64 reference), polarity 0 -> -1 like
+ * events_to_voxel_grid.  workspace: cf_preprocess_workspace_bytes(B, nb*H*W) when preprocess != NONE. */
+CF_API int cf_voxel_bin_packed(const void *packed, const int64_t *offsets, int64_t total_events,
+                        int B, int nb, int H, int W, int preprocess, float hot_thr, float *out,
+                        void *workspace, size_t workspace_bytes, cf_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
  * Part 2: flow-guided bilinear warp (a gather in BOTH warp modes)
  * replaces  utils/flow_utils.py:153-190  forwardWarp.forward  (sign = -1)
  *           utils/flow_utils.py:83-120   backWarp.forward     (sign = +1)
@@ -145,6 +161,19 @@ CF_API int cf_warp(const float *img, const float *flow, float *out, int B, int C
 CF_API int cf_warp_frame_and_codes(const float *img, const float *codes, const float *flow,
                             float *img_out, float *codes_out, int B, int Ci, int Cz,
                             int H, int W, float sign, cf_stream_t stream);
+
+/* Flow-warp of a voxel grid for the FWL metric
+ * replaces  loss.py:27-83  voxel_warping_flow_loss   (call sites test_wo_flow.py:161, test_mvsec.py:180)
+ * voxel [B,C,H,W], displacement [B,2,H,W] (ch0 = x).  Channel i is sampled (bilinear, zeros padding,
+ * align_corners=True, grid 2*coord/size - 1) at (x + dx*r_i, y + dy*r_i), r_i = i/(C-1), or 1 - i/(C-1)
+ * with the displacement negated when reverse_time != 0.
+ * warped   [B,C,H,W] the warped channels (may be NULL);  summed [B,1,H,W] their sum;
+ * mean_var device double[2] <- mean and UNBIASED variance of `summed` over the batch (may be NULL;
+ *          needs cf_voxel_flow_warp_workspace_bytes(B, H, W) bytes of workspace). */
+CF_API size_t cf_voxel_flow_warp_workspace_bytes(int B, int H, int W);
+CF_API int cf_voxel_flow_warp(const float *voxel, const float *displacement, int B, int C, int H, int W,
+                       int reverse_time, float *warped, float *summed, double *mean_var,
+                       void *workspace, size_t workspace_bytes, cf_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * Part 3: all-pairs correlation volume, pyramid and lookup

@@ -257,6 +257,29 @@ def corr_lookup(pyramid: list[torch.Tensor], coords: torch.Tensor, radius: int =
     return torch.cat(out, dim=-1).permute(0, 3, 1, 2).contiguous().float()
 
 
+def voxel_flow_warp(voxel: torch.Tensor, displacement: torch.Tensor, reverse_time: bool = False):
+    """loss.py:27-83 (voxel_warping_flow_loss) through the same library calls: one grid_sample per channel
+    over the whole grid, channel i kept.  Returns (variance, summed [N,1,H,W], warped [N,C,H,W])."""
+    if reverse_time:
+        displacement = -displacement
+    n, c, h, w = voxel.shape
+    yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    xx, yy = xx.float(), yy.float()
+    dx, dy = displacement[:, 0], displacement[:, 1]
+    inc = 1.0 / (c - 1.0)
+    summed = torch.zeros((n, 1, h, w), dtype=voxel.dtype)
+    warped = torch.zeros((n, c, h, w), dtype=voxel.dtype)
+    for i in range(c):
+        ratio = (1.0 - i * inc) if reverse_time else i * inc
+        grid = torch.stack([xx + dx * ratio, yy + dy * ratio], dim=3)
+        grid[:, :, :, 1] = (2.0 * grid[:, :, :, 1]) / h - 1.0
+        grid[:, :, :, 0] = (2.0 * grid[:, :, :, 0]) / w - 1.0
+        ch = F.grid_sample(voxel, grid, align_corners=True)[:, i:i + 1]
+        summed += ch
+        warped[:, i:i + 1] = ch
+    return summed.var(), summed, warped
+
+
 def psnr(a: torch.Tensor, b: torch.Tensor) -> float:
     """loss.py:15-24 -- 20*log10(1/sqrt(mse)), 100 when mse < 1e-10."""
     mse = float(torch.mean((a.double() - b.double()) ** 2))

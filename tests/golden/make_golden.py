@@ -17,6 +17,7 @@ voxel.npz   utils/event_process.py   all voxelisers + both preprocess variants
 warp.npz    utils/flow_utils.py      forwardWarp / backWarp / FrameWarp, + the
                                      image+codes step of e2v/e2v_model.py:188-191
 corr.npz    ERAFT/corr.py, DCEIFlow/core/corr/raft_corr.py   pyramid + lookup
+fwl.npz     loss.py                  voxel_warping_flow_loss (FWL metric), both time directions
 trace_eiflow.npz / trace_eraft.npz
             hot-path calls recorded inside DCEIFlowCistaNet / ERAFTCistaNet
             (seeded random-init weights, base_channels=16 to keep the files
@@ -120,6 +121,35 @@ def make_warp():
     bw = FrameWarp("backward")
     out["step/codes_warped_backward"] = bw.warp_frame(torch.from_numpy(z1), ds).numpy()
     save("warp.npz", **out)
+
+
+# -------------------------------------------------------------------- fwl ---
+def make_fwl():
+    """loss.voxel_warping_flow_loss (FWL metric).  loss.py imports plotting / perceptual-metric packages
+    that are absent here and unused by this function: they are stubbed with attribute-less modules."""
+    class _Any(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return object
+    for name in ("pytorch_msssim", "lpips", "skimage", "skimage.metrics"):
+        sys.modules.setdefault(name, _Any(name))
+    import loss as ref_loss
+    rng = np.random.default_rng(61)
+    ev = [synth.events(4000, 36, 44, 70 + b) for b in range(2)]
+    from utils import event_process as ep
+    voxel = np.stack([ep.events_to_voxel_grid(e.copy(), 5, 44, 36) for e in ev]).astype(np.float32)
+    disp = (3.0 * rng.standard_normal((2, 2, 36, 44))).astype(np.float32)
+    disp[0, :, :3, :3] = 40.0          # samples far outside the image: zeros padding
+    out = {"voxel": voxel, "disp": disp}
+    for rev in (False, True):
+        loss, extra = ref_loss.voxel_warping_flow_loss(torch.from_numpy(voxel), torch.from_numpy(disp), output_images=True,
+                                                       reverse_time=rev)
+        out[f"loss_{int(rev)}"] = np.float32(loss.item())
+        out[f"warped_{int(rev)}"] = extra["voxel_grid_warped"].numpy()
+    zero = ref_loss.voxel_warping_flow_loss(torch.from_numpy(voxel), torch.zeros(2, 2, 36, 44))
+    out["loss_zero_flow"] = np.float32(zero.item())
+    save("fwl.npz", **out)
 
 
 # ------------------------------------------------------------------- corr ---
@@ -253,6 +283,8 @@ if __name__ == "__main__":
         make_voxel()
     if not only or "warp" in only:
         make_warp()
+    if not only or "fwl" in only:
+        make_fwl()
     if not only or "corr" in only:
         make_corr()
     if not only or "trace" in only:

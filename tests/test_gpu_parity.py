@@ -175,6 +175,37 @@ def test_voxel_atomic_paths_ragged_batches(cuda_device, h, w, counts, path):
         assert_voxel_close(pol[b][:, 1] - pol[b][:, 0], ref, mag)       # signed recombination = plain grid
 
 
+@pytest.mark.parametrize("h,w,counts", [(180, 240, [15000, 0, 7000, 1, 15000]), (480, 640, [100000, 60000])])
+def test_voxel_packed_events(cuda_device, h, w, counts):
+    """Packed 8-byte events: host and device packers agree bit for bit; the packed voxel kernel
+    stays within the atomic-mode tolerance of the fp64 oracle, raw and with fused normalisation."""
+    wins = [synth.events(n, h, w, seed=500 + i) if n else np.zeros((0, 4)) for i, n in enumerate(counts)]
+    ev = np.concatenate(wins, axis=0)
+    ev[7, 1:3] = [-3.0, 5.0]          # out of grid -> dropped by both paths
+    wins[0][7, 1:3] = [-3.0, 5.0]
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    host = cf.pack_events_host(ev, off)
+    ev_d, off_d = dev_t(ev, cuda_device), dev_t(off, cuda_device)
+    packed = cf.pack_events(ev_d, off_d)
+    assert last_kernel() == "events_pack_kernel"
+    assert np.array_equal(packed.cpu().numpy().view(np.uint64), host)
+    up = torch.from_numpy(host.view(np.int64)).to(cuda_device)       # the ingest path: pack on the host, upload 8 B/event
+    raw = cf.events_to_voxel_grid_packed(up, off_d, 5, w, h).cpu().numpy()
+    assert last_kernel() == "voxel_scatter_packed_kernel"
+    fused = cf.events_to_voxel_grid_packed(up, off_d, 5, w, h, normalize="std", filter_hot_pixel=True).cpu().numpy()
+    for b, win in enumerate(wins):
+        if len(win) == 0:
+            assert not raw[b].any() and not fused[b].any()
+            continue
+        ok = (win[:, 1] >= 0) & (win[:, 1] < w) & (win[:, 2] >= 0) & (win[:, 2] < h)
+        ref = explicit.voxel_grid_sequential(win[ok], 5, w, h, explicit.FLAVOUR_NUMPY)
+        pos = win[ok].copy()
+        pos[:, 3] = 1.0
+        mag = explicit.voxel_grid_sequential(pos, 5, w, h, explicit.FLAVOUR_NUMPY)
+        assert_voxel_close(raw[b], ref, mag)
+        np.testing.assert_allclose(fused[b], explicit.preprocess(ref, "std", 5.0), rtol=1e-4, atol=1e-4)
+
+
 def test_voxel_is_reverse(cuda_device):
     ev = synth.events(2000, 20, 24, 5)
     got = cf.events_to_voxel_grid(ev, 5, 24, 20, is_reverse=True, mode="deterministic")
@@ -324,6 +355,37 @@ def test_warp_rejects_cpu_and_grad(cuda_device):
         cf.forwardWarp(8, 8)(g, torch.zeros(1, 2, 8, 8, device=cuda_device))
     with pytest.raises(ValueError):
         cf.warp(torch.zeros(1, 1, 8, 8, device=cuda_device), torch.zeros(1, 2, 5, 5, device=cuda_device), -1.0)
+
+
+# -------------------------------------------------------------------- fwl ---
+def test_fwl_golden_and_config_shape(golden, cuda_device):
+    """voxel_warping_flow_loss (FWL metric): warped channels within the warp tolerance
+    (1e-4 abs) of the reference's own output, variance within 1e-5 relative; then a 480x640 grid against
+    the oracle port, and the FWL ratio itself (loss(flow) / loss(0))."""
+    g = golden("fwl")
+    voxel, disp = dev_t(g["voxel"], cuda_device), dev_t(g["disp"], cuda_device)
+    for rev in (False, True):
+        loss, extra = cf.voxel_warping_flow_loss(voxel, disp, output_images=True, reverse_time=rev)
+        assert last_kernel() == "moments_finish_kernel"
+        assert loss.device.type == "cuda" and loss.dim() == 0 and loss.dtype == torch.float32
+        assert extra["voxel_grid"] is voxel
+        np.testing.assert_allclose(extra["voxel_grid_warped"].cpu().numpy(), g[f"warped_{int(rev)}"], rtol=0, atol=1e-4)
+        assert abs(loss.item() - float(g[f"loss_{int(rev)}"])) <= 1e-5 * abs(float(g[f"loss_{int(rev)}"]))
+    zero = cf.voxel_warping_flow_loss(voxel, torch.zeros_like(disp))
+    assert abs(zero.item() - float(g["loss_zero_flow"])) <= 1e-5 * float(g["loss_zero_flow"])
+    # config-5 frame, batch 2
+    ev = [synth.events(100000, 480, 640, 900 + b) for b in range(2)]
+    vox = np.stack([ref_port.voxel_grid_numpy(e, 5, 640, 480) for e in ev]).astype(np.float32)
+    _, _, flow = synth.warp_inputs(2, 480, 640, seed=17, code_channels=8, flow_kind="smooth")
+    ref_var, ref_sum, ref_warped = ref_port.voxel_flow_warp(torch.from_numpy(vox), torch.from_numpy(flow))
+    loss, extra = cf.voxel_warping_flow_loss(dev_t(vox, cuda_device), dev_t(flow, cuda_device), output_images=True)
+    assert (extra["voxel_grid_warped"].cpu() - ref_warped).abs().max().item() <= 1e-4
+    assert abs(loss.item() - ref_var.item()) <= 1e-5 * ref_var.item()
+    fwl = loss / cf.voxel_warping_flow_loss(dev_t(vox, cuda_device), torch.zeros(2, 2, 480, 640, device=cuda_device))
+    ref0, _, _ = ref_port.voxel_flow_warp(torch.from_numpy(vox), torch.zeros(2, 2, 480, 640))
+    assert abs(fwl.item() - (ref_var / ref0).item()) <= 1e-5
+    with pytest.raises(ValueError):   # the reference divides by C - 1
+        cf.voxel_warping_flow_loss(torch.zeros(1, 1, 8, 8, device=cuda_device), torch.zeros(1, 2, 8, 8, device=cuda_device))
 
 
 # ------------------------------------------------------------------- corr ---

@@ -33,7 +33,7 @@ def test_header_declares_the_expected_entry_points():
     for s in ("cf_voxel_bin", "cf_warp", "cf_warp_frame_and_codes", "cf_corr_build", "cf_corr_lookup",
               "cf_voxel_preprocess", "cf_last_error", "cf_version", "cf_device_check"):
         assert s in syms
-    assert len(syms) == 14
+    assert len(syms) == 18
 
 
 def test_library_exports_every_header_symbol(built_lib):
@@ -153,6 +153,22 @@ def test_synth_generators_are_seeded_and_well_formed():
     assert synth.padded_dims(260, 346) == (288, 352) and synth.padded_dims(480, 640) == (480, 640)
 
 
+def test_pack_events_host_layout():
+    """The host packer's record layout (include/cistaflow.h part 1b): low word float32 t - t_first_of_window,
+    high word x | y << 16 | p << 31; out-of-range coordinates are marked with x = 0xffff."""
+    import cistaflow_b200 as cf
+    ev = np.array([[1000.0, 3, 4, 1], [1000.0 + 2.5e-3, 239, 179, 0], [2000.0, 7, 8, 1], [2000.25, -1, 2, 0]])
+    off = np.array([0, 2, 4])
+    rec = cf.pack_events_host(ev, off)
+    assert rec.dtype == np.uint64 and rec.shape == (4,)
+    lo = (rec & np.uint64(0xffffffff)).astype(np.uint32).view(np.float32)
+    hi = (rec >> np.uint64(32)).astype(np.uint32)
+    np.testing.assert_array_equal(lo, np.array([0.0, 2.5e-3, 0.0, 0.25], np.float32))   # stamps relative to each window
+    assert lo[1] == np.float32(np.float64(1000.0 + 2.5e-3) - 1000.0) != np.float32(1000.0 + 2.5e-3) - np.float32(1000.0)
+    assert list(hi & 0xffff) == [3, 239, 7, 0xffff] and list((hi >> 16) & 0x7fff) == [4, 179, 8, 0]
+    assert list(hi >> 31) == [1, 0, 1, 0]
+
+
 def test_shard_streams_partition():
     from cistaflow_b200 import sharding
     for n, world in ((64, 1), (64, 8), (10, 4), (3, 8)):
@@ -182,7 +198,7 @@ t = sharding.max_over_ranks(1.0 + rank, torch.device("cpu"))
 assert t == float(world)
 dist.barrier()
 dist.destroy_process_group()
-print("OK", rank)
+os.write(1, f"OK {rank}\n".encode())  # one write(2): atomic on a pipe, the two ranks cannot interleave
 """
 
 

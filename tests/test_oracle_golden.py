@@ -143,3 +143,17 @@ def test_model_trace_replay_through_oracle(golden, trace):
     # the codes were warped with the x0.5 down-sampled flow (e2v/e2v_model.py:190)
     half = ref_port.downsample_flow(torch.from_numpy(g["flow_final"]))
     assert np.array_equal(half.numpy(), g["warp1/flow"])
+
+
+def test_fwl_ref_port_bit_exact(golden):
+    """loss.voxel_warping_flow_loss (FWL metric): the port reproduces the reference's warped channels and
+    variance bit for bit, both time directions, and its zero-flow denominator."""
+    g = golden("fwl")
+    voxel, disp = torch.from_numpy(g["voxel"]), torch.from_numpy(g["disp"])
+    for rev in (False, True):
+        var, summed, warped = ref_port.voxel_flow_warp(voxel, disp, reverse_time=rev)
+        assert np.array_equal(warped.numpy(), g[f"warped_{int(rev)}"])
+        assert np.float32(var.item()) == g[f"loss_{int(rev)}"]
+    var0, _, _ = ref_port.voxel_flow_warp(voxel, torch.zeros_like(disp))
+    assert np.float32(var0.item()) == g["loss_zero_flow"]
+
