@@ -11,11 +11,11 @@ namespace cf {
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 
-static thread_local const char *g_last_kernel = "";
+static std::atomic<const char *> g_last_kernel{""};   // process-wide: autograd runs backward kernels on its own thread
 
 void count_launch(const char *kernel) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    g_last_kernel = kernel;
+    g_last_kernel.store(kernel, std::memory_order_relaxed);
 }
 
 void set_error(const char *fmt, ...) {
@@ -80,6 +80,6 @@ int cf_device_check(void) { return cf::check_device(); }
 
 int64_t cf_launch_count(void) { return cf::g_launches.load(std::memory_order_relaxed); }
 
-const char *cf_last_kernel(void) { return cf::g_last_kernel; }
+const char *cf_last_kernel(void) { return cf::g_last_kernel.load(std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -8,8 +8,10 @@ serves both.  ``warp_frame_and_codes`` is the fused per-frame step of
 ``e2v/e2v_model.py:188-191`` (image + sparse codes, x0.5 flow down-sampling
 done inside the kernel).
 
-Inference only: the kernels have no backward (the reference's evaluation
-drivers run under ``torch.no_grad()``); a tensor that requires grad raises.
+Autograd: ``warp`` (hence ``backWarp`` / ``forwardWarp`` / ``FrameWarp.warp_frame``) is differentiable
+w.r.t. both the image and the flow -- the backward is ``cf_warp_backward``, the bilinear splat (the
+reference trains through these modules, loss.py:147,336,398).  The fused ``warp_frame_and_codes`` step is
+inference-only (the evaluation drivers run under ``torch.no_grad()``).
 """
 from __future__ import annotations
 
@@ -19,23 +21,57 @@ import torch.nn as nn
 from . import _lib
 
 
-def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
+def _prep(t: torch.Tensor, name: str, allow_grad: bool = False) -> torch.Tensor:
     _lib.require_cuda(t, name)
-    if torch.is_grad_enabled() and t.requires_grad:
-        raise RuntimeError(f"cistaflow_b200 warp is inference-only: {name} requires grad "
-                           f"(run under torch.no_grad(); the backward/splat kernel is not built yet)")
+    if not allow_grad and torch.is_grad_enabled() and t.requires_grad:
+        raise RuntimeError(f"cistaflow_b200 warp_frame_and_codes is inference-only: {name} requires grad "
+                           f"(run under torch.no_grad(), or use warp() / FrameWarp.warp_frame, which are differentiable)")
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
 
 
+class _WarpFunction(torch.autograd.Function):
+    """cf_warp forward, cf_warp_backward (bilinear splat + flow gradient) backward."""
+
+    @staticmethod
+    def forward(ctx, img, flow, sign):
+        ctx.sign = float(sign)
+        ctx.save_for_backward(img, flow)
+        return _warp_forward(img, flow, sign, None)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        img, flow = ctx.saved_tensors
+        need_img, need_flow = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        grad_out = grad_out.float().contiguous()
+        B, C, H, W = img.shape
+        grad_img = torch.empty_like(img) if need_img else None
+        grad_flow = torch.empty_like(flow) if need_flow else None
+        lib = _lib.load()
+        with torch.cuda.device(img.device):
+            rc = lib.cf_warp_backward(grad_out.data_ptr(), img.data_ptr(), flow.data_ptr(), _lib.ptr(grad_img),
+                                      _lib.ptr(grad_flow), B, C, H, W, flow.shape[2], flow.shape[3], ctx.sign,
+                                      _lib.stream_ptr(img.device))
+        _lib.check(rc, "cf_warp_backward")
+        return grad_img, grad_flow, None
+
+
 def warp(img: torch.Tensor, flow: torch.Tensor, sign: float, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Differentiable front end of ``cf_warp`` (see ``_warp_forward`` for the maths)."""
+    if torch.is_grad_enabled() and (img.requires_grad or flow.requires_grad):
+        assert out is None, "out= is not supported when gradients are recorded"
+        return _WarpFunction.apply(_prep(img, "img", True), _prep(flow, "flow", True), sign)
+    return _warp_forward(img, flow, sign, out)
+
+
+def _warp_forward(img: torch.Tensor, flow: torch.Tensor, sign: float, out: torch.Tensor | None = None) -> torch.Tensor:
     """out[b,c,y,x] = bilinear(img[b,c], reflect((x+sign*u)(W-1)/W, (y+sign*v)(H-1)/H)).
 
     ``flow`` is either at the image's resolution or at twice the resolution
     (then the reference's x0.5 bilinear align_corners=True down-sampling is
     fused, values not rescaled)."""
-    img, flow = _prep(img, "img"), _prep(flow, "flow")
+    img, flow = _prep(img, "img", True), _prep(flow, "flow", True)
     assert img.dim() == 4 and flow.dim() == 4 and flow.shape[1] == 2 and flow.shape[0] == img.shape[0]
     assert img.device == flow.device
     B, C, H, W = img.shape

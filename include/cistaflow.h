@@ -59,7 +59,7 @@ CF_API int cf_device_check(void);
  * capture) in this process so far; benchmarks report it as evidence that the
  * hand-written kernels -- not a fallback -- did the work. */
 CF_API int64_t cf_launch_count(void);
-/* Name of the kernel this thread launched last ("" before the first launch): lets tests assert
+/* Name of the kernel this process launched last ("" before the first launch): lets tests assert
  * WHICH of the data-movement variants of an entry point ran (e.g. the TMA-staged warp kernel
  * vs the direct gather it falls back to on discontinuous flow). */
 CF_API const char *cf_last_kernel(void);
@@ -161,6 +161,16 @@ CF_API int cf_warp(const float *img, const float *flow, float *out, int B, int C
 CF_API int cf_warp_frame_and_codes(const float *img, const float *codes, const float *flow,
                             float *img_out, float *codes_out, int B, int Ci, int Cz,
                             int H, int W, float sign, cf_stream_t stream);
+
+/* Adjoint of cf_warp: what autograd runs through forwardWarp / backWarp in
+ * training (loss.py:147,336,398; train.py:208-232).  grad_out [B,C,H,W];
+ *   grad_img  [B,C,H,W]           <- bilinear SPLAT of grad_out into the 4 taps (may be NULL)
+ *   grad_flow [B,2,flowH,flowW]   <- through reflect/clip and the 2*(x/W-0.5) normalisation; with the fused x0.5
+ *                                    down-sampling (H == flowH/2) its adjoint is applied too (may be NULL; needs img)
+ * Both outputs are zeroed by the call; accumulation order is unspecified (fp32 atomics), as in ATen's CUDA backward. */
+CF_API int cf_warp_backward(const float *grad_out, const float *img, const float *flow, float *grad_img,
+                     float *grad_flow, int B, int C, int H, int W, int flowH, int flowW, float sign,
+                     cf_stream_t stream);
 
 /* Flow-warp of a voxel grid for the FWL metric
  * replaces  loss.py:27-83  voxel_warping_flow_loss   (call sites test_wo_flow.py:161, test_mvsec.py:180)

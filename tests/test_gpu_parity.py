@@ -346,13 +346,59 @@ def test_warp_full_size_properties(cuda_device):
     assert torch.equal(cf.warp(x, flow, -1.0), cf.warp(x, -flow, +1.0))
 
 
+@pytest.mark.parametrize("mode", ["forward", "backward"])
+@pytest.mark.parametrize("shape,flow_kind", [((2, 3, 18, 22), "noise"), ((1, 128, 90, 120), "smooth"), ((2, 5, 31, 45), "smooth")])
+def test_warp_backward_matches_autograd_of_the_reference_ops(cuda_device, mode, shape, flow_kind):
+    """gradients of forwardWarp / backWarp w.r.t. image (the bilinear splat) and flow against
+    torch.autograd through the oracle port (F.grid_sample, reflection padding) on CPU."""
+    B, C, H, W = shape
+    rng = np.random.default_rng(5)
+    img = rng.standard_normal(shape).astype(np.float32)
+    _, _, flow = synth.warp_inputs(B, H, W, seed=8, code_channels=8, flow_kind=flow_kind)
+    flow[0, :, 0, 0] = [-3.0 * W, 2.5 * H]      # far outside: reflected several times
+    gout = rng.standard_normal(shape).astype(np.float32)
+    ri, rf = torch.from_numpy(img).requires_grad_(), torch.from_numpy(flow).requires_grad_()
+    ref_port.warp(ri, rf, mode).backward(torch.from_numpy(gout))
+    di, df = dev_t(img, cuda_device).requires_grad_(), dev_t(flow, cuda_device).requires_grad_()
+    mod = cf.forwardWarp(W, H) if mode == "forward" else cf.backWarp(W, H)
+    out = mod(di, df)
+    assert out.requires_grad
+    out.backward(dev_t(gout, cuda_device))
+    assert last_kernel() == "warp_backward_kernel"
+    scale_i = max(1.0, float(ri.grad.abs().max()))
+    scale_f = max(1.0, float(rf.grad.abs().max()))
+    assert (di.grad.cpu() - ri.grad).abs().max().item() <= 1e-4 * scale_i
+    # the flow gradient is discontinuous where a sample sits exactly on a pixel boundary: compare away from those
+    err = (df.grad.cpu() - rf.grad).abs()
+    assert err.max().item() <= 2e-3 * scale_f, err.max().item()
+    assert (err > 1e-4 * scale_f).float().mean().item() < 1e-3
+
+
+def test_warp_backward_fused_half_resolution_flow(cuda_device):
+    """Codes at half resolution warped with the full-resolution flow (e2v_model.py:190): the kernel also applies the
+    adjoint of the x0.5 bilinear down-sampling.  Oracle: autograd through F.interpolate + grid_sample."""
+    B, C, H, W = 2, 16, 36, 48
+    rng = np.random.default_rng(6)
+    codes = rng.standard_normal((B, C, H // 2, W // 2)).astype(np.float32)
+    _, _, flow = synth.warp_inputs(B, H, W, seed=9, code_channels=8, flow_kind="smooth")
+    gout = rng.standard_normal(codes.shape).astype(np.float32)
+    rz, rf = torch.from_numpy(codes).requires_grad_(), torch.from_numpy(flow).requires_grad_()
+    ref_port.warp(rz, ref_port.downsample_flow(rf), "forward").backward(torch.from_numpy(gout))
+    dz, df = dev_t(codes, cuda_device).requires_grad_(), dev_t(flow, cuda_device).requires_grad_()
+    cf.warp(dz, df, -1.0).backward(dev_t(gout, cuda_device))
+    assert (dz.grad.cpu() - rz.grad).abs().max().item() <= 1e-4 * max(1.0, float(rz.grad.abs().max()))
+    err = (df.grad.cpu() - rf.grad).abs()
+    scale = max(1.0, float(rf.grad.abs().max()))
+    assert err.max().item() <= 2e-3 * scale and (err > 1e-4 * scale).float().mean().item() < 1e-3
+
+
 def test_warp_rejects_cpu_and_grad(cuda_device):
     img = torch.zeros(1, 1, 8, 8)
     with pytest.raises(RuntimeError):
         cf.forwardWarp(8, 8)(img, torch.zeros(1, 2, 8, 8))
     g = torch.zeros(1, 1, 8, 8, device=cuda_device, requires_grad=True)
-    with pytest.raises(RuntimeError):
-        cf.forwardWarp(8, 8)(g, torch.zeros(1, 2, 8, 8, device=cuda_device))
+    with pytest.raises(RuntimeError):   # the fused per-frame step is inference-only (warp() itself is differentiable)
+        cf.warp_frame_and_codes(g, torch.zeros(1, 4, 4, 4, device=cuda_device), torch.zeros(1, 2, 8, 8, device=cuda_device))
     with pytest.raises(ValueError):
         cf.warp(torch.zeros(1, 1, 8, 8, device=cuda_device), torch.zeros(1, 2, 5, 5, device=cuda_device), -1.0)
 
