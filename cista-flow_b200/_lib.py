@@ -47,6 +47,7 @@ SYMBOLS = {
     "cf_corr_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "cf_corr_build": (_i, [_vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _i, _vp, _sz, _vp]),
     "cf_corr_lookup": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "cf_corr_lookup_backward": (_i, [_vp, ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp, _vp]),
 }
 
 _lock = threading.Lock()

@@ -30,8 +30,6 @@ def coords_grid(batch, ht, wd, device=None):
 
 def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
     _lib.require_cuda(t, name)
-    if torch.is_grad_enabled() and t.requires_grad:
-        raise RuntimeError(f"cistaflow_b200 CorrBlock is inference-only: {name} requires grad")
     return t.float().contiguous()
 
 
@@ -79,16 +77,86 @@ def lookup(pyramid, coords: torch.Tensor, radius: int, out: torch.Tensor | None 
     return out
 
 
+class _PyramidFunction(torch.autograd.Function):
+    """Forward: cf_corr_build.  Backward (training): the level gradients are folded into the
+    level-0 volume through the adjoint of avg_pool2d(2, 2) (each pooled cell spreads g/4 to its 2x2 window; a
+    floored odd row/column gets nothing) and the two feature-map gradients are plain GEMMs
+    (grad_f1 = f2 . G^T / sqrt(D), grad_f2 = f1 . G / sqrt(D)) -- torch.matmul, a library GEMM, like the reference's."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, num_levels, precision):
+        ctx.save_for_backward(fmap1, fmap2)
+        pyramid = build_pyramid(fmap1, fmap2, num_levels, precision)
+        return tuple(pyramid)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        fmap1, fmap2 = ctx.saved_tensors
+        B, D, h, w = fmap1.shape
+        N = h * w
+        total = None
+        for l in reversed(range(len(grads))):
+            g = grads[l]
+            if total is not None:   # adjoint of avg_pool2d: level l+1 -> level l
+                hl, wl = h >> l, w >> l
+                up = torch.nn.functional.interpolate(total, scale_factor=2, mode="nearest") * 0.25
+                up = torch.nn.functional.pad(up, (0, wl - up.shape[3], 0, hl - up.shape[2]))
+                total = up if g is None else up + g
+            elif g is not None:
+                total = g.float()
+        if total is None:
+            return None, None, None, None
+        G = total.reshape(B, N, N) / float(D) ** 0.5          # d loss / d (f1^T f2)
+        f1, f2 = fmap1.reshape(B, D, N).float(), fmap2.reshape(B, D, N).float()
+        grad_f1 = torch.matmul(f2, G.transpose(1, 2)).reshape(B, D, h, w) if ctx.needs_input_grad[0] else None
+        grad_f2 = torch.matmul(f1, G).reshape(B, D, h, w) if ctx.needs_input_grad[1] else None
+        return grad_f1, grad_f2, None, None
+
+
+class _LookupFunction(torch.autograd.Function):
+    """Forward: cf_corr_lookup.  Backward: cf_corr_lookup_backward (patch gradients by gather, coordinate gradient)."""
+
+    @staticmethod
+    def forward(ctx, coords, radius, *pyramid):
+        ctx.radius = radius
+        ctx.save_for_backward(coords, *pyramid)
+        return lookup(list(pyramid), coords, radius)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        coords, *pyramid = ctx.saved_tensors
+        B, _, h, w = coords.shape
+        levels = len(pyramid)
+        want_coords = ctx.needs_input_grad[0]
+        want_pyr = any(ctx.needs_input_grad[2:])
+        grad_out = grad_out.float().contiguous()
+        grad_coords = torch.empty_like(coords) if want_coords else None
+        grad_pyr = [torch.empty_like(p) for p in pyramid] if want_pyr else None
+        lib = _lib.load()
+        with torch.cuda.device(coords.device):
+            rc = lib.cf_corr_lookup_backward(grad_out.data_ptr(), _lib.pointer_array(pyramid), coords.data_ptr(), B, h, w,
+                                             levels, ctx.radius, _lib.pointer_array(grad_pyr) if want_pyr else None,
+                                             _lib.ptr(grad_coords), _lib.stream_ptr(coords.device))
+        _lib.check(rc, "cf_corr_lookup_backward")
+        return (grad_coords, None, *(grad_pyr if want_pyr else [None] * levels))
+
+
 class CorrBlock:
-    """Drop-in for ``ERAFT/corr.py:12-60`` / ``raft_corr.py:15-65``."""
+    """Drop-in for ``ERAFT/corr.py:12-60`` / ``raft_corr.py:15-65``.  Differentiable like the reference's:
+    gradients reach the feature maps and the lookup coordinates when they are being recorded."""
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, precision=None):
         self.num_levels = num_levels
         self.radius = radius
-        with torch.no_grad():
-            self.corr_pyramid = build_pyramid(fmap1, fmap2, num_levels, precision)
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            self.corr_pyramid = list(_PyramidFunction.apply(_prep(fmap1, "fmap1"), _prep(fmap2, "fmap2"), num_levels, precision))
+        else:
+            with torch.no_grad():
+                self.corr_pyramid = build_pyramid(fmap1, fmap2, num_levels, precision)
 
     def __call__(self, coords):
+        if torch.is_grad_enabled() and (coords.requires_grad or any(p.requires_grad for p in self.corr_pyramid)):
+            return _LookupFunction.apply(_prep(coords, "coords"), self.radius, *self.corr_pyramid)
         with torch.no_grad():
             return lookup(self.corr_pyramid, coords, self.radius)
 

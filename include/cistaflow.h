@@ -219,6 +219,15 @@ CF_API int cf_corr_build(const float *fmap1, const float *fmap2, int B, int D, i
 CF_API int cf_corr_lookup(const float *const *pyramid, const float *coords, int B, int h, int w,
                    int levels, int radius, float *out, cf_stream_t stream);
 
+/* Adjoint of cf_corr_lookup (training through CorrBlock.__call__).
+ * grad_out [B, levels*(2r+1)^2, h, w];
+ *   grad_pyramid[l] [B*h*w, 1, h>>l, w>>l]  (host array of device pointers; zeroed by the call; may be NULL)
+ *   grad_coords     [B, 2, h, w]            (may be NULL; needs `pyramid`)
+ * No atomics: every query owns its maps, each patch element is written once. */
+CF_API int cf_corr_lookup_backward(const float *grad_out, const float *const *pyramid, const float *coords,
+                            int B, int h, int w, int levels, int radius, float *const *grad_pyramid,
+                            float *grad_coords, cf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -470,6 +470,34 @@ def test_corr_golden_odd_sizes(golden, cuda_device):
         assert corr_err(blk_tc.corr_pyramid[l].cpu().numpy(), g[f"odd/pyr{l}"]) <= 1e-3
 
 
+@pytest.mark.parametrize("h,w,levels,radius", [(16, 24, 4, 4), (15, 20, 3, 3)])
+def test_corr_block_backward_matches_autograd_of_the_reference_ops(cuda_device, h, w, levels, radius):
+    """gradients through CorrBlock (pyramid build + lookup) w.r.t. both feature maps and the
+    lookup coordinates, against torch.autograd through the oracle port on CPU (fp32 correlation path)."""
+    rng = np.random.default_rng(12)
+    B, D = 2, 64
+    f1 = rng.standard_normal((B, D, h, w)).astype(np.float32)
+    f2 = rng.standard_normal((B, D, h, w)).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
+    coords = (np.stack([xs, ys])[None] + 2.5 * rng.standard_normal((B, 2, h, w))).astype(np.float32)
+    coords[0, :, 0, 0] = [-7.3, h + 5.2]     # window partly / wholly outside the map
+    k = 2 * radius + 1
+    gout = rng.standard_normal((B, levels * k * k, h, w)).astype(np.float32)
+    rf1, rf2, rc = (torch.from_numpy(a).requires_grad_() for a in (f1, f2, coords))
+    ref_port.corr_lookup(ref_port.corr_pyramid(rf1, rf2, levels), rc, radius).backward(torch.from_numpy(gout))
+    df1, df2, dc = (dev_t(a, cuda_device).requires_grad_() for a in (f1, f2, coords))
+    blk = cf.CorrBlock(df1, df2, num_levels=levels, radius=radius, precision="fp32")
+    out = blk(dc)
+    assert out.requires_grad
+    out.backward(dev_t(gout, cuda_device))
+    for got, ref, name in ((df1.grad, rf1.grad, "fmap1"), (df2.grad, rf2.grad, "fmap2")):
+        assert corr_err(got.cpu().numpy(), ref.numpy()) <= 1e-4, name
+    # the coordinate gradient jumps where a sample sits on a pixel boundary: compare away from those
+    err = (dc.grad.cpu() - rc.grad).abs()
+    scale = float(rc.grad.abs().max())
+    assert err.max().item() <= 2e-3 * scale and (err > 1e-4 * scale).float().mean().item() < 1e-3
+
+
 def test_lookup_on_reference_pyramid(golden, cuda_device):
     """Feed the REFERENCE's pyramid to our lookup: isolates the gather from the GEMM."""
     g = golden("corr")
