@@ -87,7 +87,7 @@ __device__ __forceinline__ void trace_at(int slot) {
     if (g_trace && slot < kTraceSlots) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_trace[(size_t)blockIdx.x * kTraceSlots + slot] = t;
+        g_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kTraceSlots + slot] = t;
     }
 }
 #define CF_TRACE_AT(slot) cf::trace_at(slot)

@@ -39,15 +39,126 @@ struct Pyramid {
 
 constexpr int kLookupThreads = 256;
 
-// RADIUS/LEVELS > 0: compile-time radius / level count (the models use 4 / 4);
-// 0: use the runtime arguments.
-template <int RADIUS, int LEVELS, int QT>
+// ---- the models' configuration (4 levels, radius 4) -----------------------------------------
+// The kernel is instruction-issue and latency bound at feature-map sizes (6 144 queries at
+// configs[1]); both phases are written for few instructions per element:
+//   phase A  warp <-> query, lane <-> (patch column = lane % 10, row group = lane / 10): a lane walks
+//            rows rg, rg+3, rg+6, rg+9 of its column, so the x bound, the column address and the
+//            shared-memory slot are loop constants and a row costs one compare + one predicated LDG;
+//            the 16 loads of a query (two queries per pass: 32 per lane) are issued before the
+//            first shared-memory store;
+//   phase B  thread <-> (query = lane, task = (level, window column i)): the 9 samples of a window
+//            column share their horizontal interpolation, so a task is 20 LDS + 10 horizontal + 9
+//            vertical lerps and 9 coalesced stores (32 lanes = 32 consecutive queries of one channel
+//            = one 128-byte line of the channel-major output) instead of 36 LDS + 36 FMA.
+template <int QT>
+__global__ void __launch_bounds__(kLookupThreads)
+corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict__ coords, float *__restrict__ out, int N) {
+    extern __shared__ float smem[];
+    constexpr int PS = 401;                    // 4 levels x 10 x 10, odd stride between queries
+    constexpr int NW = kLookupThreads / 32;
+    constexpr int QPW = QT / NW;               // queries gathered by one warp
+    constexpr int U = 2;                       // queries in flight per pass
+    static_assert(QPW % U == 0, "queries per warp must be even");
+    float *patch = smem;                       // [QT][PS]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * QT;
+    const float *cb = coords + (size_t)b * 2 * N;
+    if (tid == 0) CF_TRACE_AT(0);
+
+    // phase-B coordinates of this lane's query: requested now, first used after the barrier
+    const int qiB = lane % QT, qB = q0 + qiB;
+    float cxB = 0.f, cyB = 0.f;
+    if (qB < N) {
+        cxB = __ldg(cb + qB);
+        cyB = __ldg(cb + N + qB);
+    }
+
+    // ---- phase A ---------------------------------------------------------------------------
+    {
+        // clamp keeps (int) conversions defined for wild coordinates; anything this far out samples
+        // only zero padding anyway (NaN clamps to the bound)
+        float cxs[QPW], cys[QPW];
+#pragma unroll
+        for (int u = 0; u < QPW; ++u) {
+            const int q = q0 + warp * QPW + u;
+            cxs[u] = q < N ? fminf(fmaxf(__ldg(cb + q), -1.0e6f), 1.0e6f) : 0.f;
+            cys[u] = q < N ? fminf(fmaxf(__ldg(cb + N + q), -1.0e6f), 1.0e6f) : 0.f;
+        }
+        const int rg = lane / 10, col = lane - rg * 10;    // rg == 3: lanes 30, 31 idle
+        float *slot = patch + (warp * QPW) * PS + rg * 10 + col;
+#pragma unroll
+        for (int qq = 0; qq < QPW; qq += U) {
+            float v[U][16];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + warp * QPW + qq + u;
+                const bool okq = q < N && rg < 3;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const float inv = 1.f / (float)(1 << l);  // exact: coords / 2**l
+                    const int X = (int)floorf(cxs[qq + u] * inv) - 4 + col;
+                    const int Y = (int)floorf(cys[qq + u] * inv) - 4 + rg;
+                    const int Hl = pyr.H[l], Wl = pyr.W[l];
+                    const bool okx = okq && (unsigned)X < (unsigned)Wl;
+                    const float *p = pyr.ptr[l] + ((size_t)b * N + q) * (Hl * Wl) + (Y * Wl + X);
+                    asm volatile("" : "+l"(p));  // one 64-bit column address per (query, level); rows are p + 3k*Wl
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool ok = okx && (unsigned)(Y + 3 * k) < (unsigned)Hl && (k < 3 || rg == 0);
+                        v[u][l * 4 + k] = ok ? __ldg(p + 3 * k * Wl) : 0.f;
+                    }
+                }
+            }
+            if (rg < 3) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < 3 || rg == 0) slot[(qq + u) * PS + l * 100 + 30 * k] = v[u][l * 4 + k];
+            }
+        }
+    }
+    if (tid == 0) CF_TRACE_AT(1);
+    __syncthreads();
+    if (tid == 0) CF_TRACE_AT(2);
+
+    // ---- phase B ---------------------------------------------------------------------------
+    if (qB < N) {
+        constexpr int TPW = 32 / QT;               // tasks per warp pass
+        const float cx = fminf(fmaxf(cxB, -1.0e6f), 1.0e6f), cy = fminf(fmaxf(cyB, -1.0e6f), 1.0e6f);
+        const float *pq = patch + qiB * PS;
+        float *ob = out + (size_t)b * 324 * N + qB;
+#pragma unroll 1
+        for (int task = warp * TPW + lane / QT; task < 36; task += NW * TPW) {
+            const int l = task / 9, i = task - l * 9;    // i -> x offset (transposed window)
+            const float inv = 1.f / (float)(1 << l);
+            const float sx = cx * inv, sy = cy * inv;
+            const float fx = sx - floorf(sx), fy = sy - floorf(sy);
+            const float gx = 1.f - fx, gy = 1.f - fy;
+            const float *pp = pq + l * 100 + i;
+            float *o = ob + (size_t)(l * 81 + i * 9) * N;
+            float top = pp[0] * gx + pp[1] * fx;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {               // j -> y offset
+                const float bot = pp[(j + 1) * 10] * gx + pp[(j + 1) * 10 + 1] * fx;
+                o[(size_t)j * N] = top * gy + bot * fy;
+                top = bot;
+            }
+        }
+    }
+    if (tid == 0) CF_TRACE_AT(3);
+}
+
+// Generic radius / level count (runtime arguments): one element per thread and step.
+template <int QT>
 __global__ void __launch_bounds__(kLookupThreads)
 corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict__ coords, float *__restrict__ out,
-                   int N, int levels_rt, int radius_rt) {
+                   int N, int levels, int r) {
     extern __shared__ float smem[];
-    const int r = RADIUS > 0 ? RADIUS : radius_rt;
-    const int levels = LEVELS > 0 ? LEVELS : levels_rt;
     const int K = 2 * r + 1, P = K + 1, KK = K * K, PP = P * P;
     const int LPP = levels * PP;
     const int PS = LPP | 1;              // odd stride between queries
@@ -57,87 +168,31 @@ corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict_
     const int b = blockIdx.y;
     const int q0 = blockIdx.x * QT;
     const float *cb = coords + (size_t)b * 2 * N;
-    if (tid == 0) CF_TRACE_AT(0);
     if (tid < QT) {
         const int q = q0 + tid;
-        // clamp keeps (int) conversions defined for wild coordinates; anything
-        // this far out samples only zero padding anyway (NaN clamps to the bound)
         cxy[2 * tid] = q < N ? fminf(fmaxf(__ldg(cb + q), -1.0e6f), 1.0e6f) : 0.f;
         cxy[2 * tid + 1] = q < N ? fminf(fmaxf(__ldg(cb + N + q), -1.0e6f), 1.0e6f) : 0.f;
     }
-    if constexpr (!(RADIUS == 4 && LEVELS == 4)) __syncthreads();  // the generic gather reads cxy[]
+    __syncthreads();
 
     // ---- phase A: gather the patches (zero outside the map) ----------------------
-    if constexpr (RADIUS == 4 && LEVELS == 4) {
-        // warp <-> query, lane <-> patch element; per level the 100 elements are covered by 4
-        // rounds of 32 lanes, so level, row and column of a lane's element are loop constants
-        // and the 16 loads of a query are all in flight before the first shared-memory store.
-        constexpr int QPW = QT / (kLookupThreads / 32);
-        const int warp = tid >> 5, lane = tid & 31;
-        int py[4], px[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int e = lane + 32 * t;
-            py[t] = e / 10;
-            px[t] = e - py[t] * 10;
-        }
-        // two queries per pass: 32 independent loads per lane are in flight before the first store
-        constexpr int U = 2;
-        static_assert(QPW % U == 0, "queries per warp must be even");
-#pragma unroll 1
-        for (int qq = 0; qq < QPW; qq += U) {
-            float v[U][16];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int qi = warp * QPW + qq + u, q = q0 + qi;
-                // lane-uniform loads straight from global: phase A does not wait for the cxy[] staging
-                const float cx = q < N ? fminf(fmaxf(__ldg(cb + q), -1.0e6f), 1.0e6f) : 0.f;
-                const float cy = q < N ? fminf(fmaxf(__ldg(cb + N + q), -1.0e6f), 1.0e6f) : 0.f;
-#pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    const float inv = 1.f / (float)(1 << l);  // exact: coords / 2**l
-                    const int X0 = (int)floorf(cx * inv) - 4, Y0 = (int)floorf(cy * inv) - 4;
-                    const int Hl = pyr.H[l], Wl = pyr.W[l];
-                    const float *base = pyr.ptr[l] + ((size_t)b * N + q) * Hl * Wl;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int X = X0 + px[t], Y = Y0 + py[t];
-                        const bool ok = q < N && (lane + 32 * t) < 100 && X >= 0 && X < Wl && Y >= 0 && Y < Hl;
-                        v[u][l * 4 + t] = ok ? __ldg(base + Y * Wl + X) : 0.f;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int qi = warp * QPW + qq + u;
-#pragma unroll
-                for (int l = 0; l < 4; ++l)
-#pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        if (lane + 32 * t < 100) patch[qi * PS + l * 100 + lane + 32 * t] = v[u][l * 4 + t];
-            }
-        }
-    } else {
-        const int total = QT * LPP;
+    const int total = QT * LPP;
 #pragma unroll 5
-        for (int idx = tid; idx < total; idx += kLookupThreads) {
-            const int qi = idx / LPP, e = idx - qi * LPP;
-            const int l = e / PP, rem = e - l * PP;
-            const int py = rem / P, px = rem - py * P;
-            const float inv = 1.f / (float)(1 << l);  // exact: coords / 2**l
-            const int X = (int)floorf(cxy[2 * qi] * inv) - r + px;
-            const int Y = (int)floorf(cxy[2 * qi + 1] * inv) - r + py;
-            const int Hl = pyr.H[l], Wl = pyr.W[l];
-            const int q = q0 + qi;
-            float v = 0.f;
-            if (q < N && X >= 0 && X < Wl && Y >= 0 && Y < Hl)
-                v = __ldg(pyr.ptr[l] + (((size_t)b * N + q) * Hl + Y) * Wl + X);
-            patch[qi * PS + e] = v;
-        }
+    for (int idx = tid; idx < total; idx += kLookupThreads) {
+        const int qi = idx / LPP, e = idx - qi * LPP;
+        const int l = e / PP, rem = e - l * PP;
+        const int py = rem / P, px = rem - py * P;
+        const float inv = 1.f / (float)(1 << l);  // exact: coords / 2**l
+        const int X = (int)floorf(cxy[2 * qi] * inv) - r + px;
+        const int Y = (int)floorf(cxy[2 * qi + 1] * inv) - r + py;
+        const int Hl = pyr.H[l], Wl = pyr.W[l];
+        const int q = q0 + qi;
+        float v = 0.f;
+        if (q < N && X >= 0 && X < Wl && Y >= 0 && Y < Hl)
+            v = __ldg(pyr.ptr[l] + (((size_t)b * N + q) * Hl + Y) * Wl + X);
+        patch[qi * PS + e] = v;
     }
-    if (tid == 0) CF_TRACE_AT(1);
     __syncthreads();
-    if (tid == 0) CF_TRACE_AT(2);
 
     // ---- phase B: bilinear samples, coalesced channel-major stores ---------------
     constexpr int CPW = 32 / QT;                      // channels per warp-iteration
@@ -150,64 +205,48 @@ corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict_
     const float *pq = patch + qi * PS;
     float *ob = out + (size_t)b * levels * KK * N + q;
     if (q < N) {
-        if constexpr (RADIUS == 4 && LEVELS == 4) {
-            // the (<= 11) channels of this thread are the same in every level: resolve their window
-            // position once, then each sample is 4 LDS + 4 FMA + 1 STG of straight-line code
-            constexpr int NCH = (81 + c_step - 1) / c_step;
-            int offs[NCH];
-#pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                const int c = c_first + k * c_step;
-                const int i = c / 9, j = c - i * 9;  // i -> x offset, j -> y offset (transposed window)
-                offs[k] = j * 10 + i;
-            }
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                const float inv = 1.f / (float)(1 << l);
-                const float sx = cx * inv, sy = cy * inv;
-                const float fx = sx - floorf(sx), fy = sy - floorf(sy);
-                const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
-                const float *pl = pq + l * 100;
-                float *ol = ob + (size_t)(l * 81 + c_first) * N;
-#pragma unroll
-                for (int k = 0; k < NCH; ++k) {
-                    if (c_first + k * c_step < 81) {
-                        const float *pp = pl + offs[k];
-                        float acc = pp[0] * w00;
-                        acc += pp[1] * w01;
-                        acc += pp[10] * w10;
-                        acc += pp[11] * w11;
-                        ol[(size_t)(k * c_step) * N] = acc;
-                    }
-                }
-            }
-        } else {
-            for (int l = 0; l < levels; ++l) {
-                const float inv = 1.f / (float)(1 << l);
-                const float sx = cx * inv, sy = cy * inv;
-                const float fx = sx - floorf(sx), fy = sy - floorf(sy);
-                const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
-                const float *pl = pq + l * PP;
-                float *ol = ob + (size_t)l * KK * N;
+        for (int l = 0; l < levels; ++l) {
+            const float inv = 1.f / (float)(1 << l);
+            const float sx = cx * inv, sy = cy * inv;
+            const float fx = sx - floorf(sx), fy = sy - floorf(sy);
+            const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+            const float *pl = pq + l * PP;
+            float *ol = ob + (size_t)l * KK * N;
 #pragma unroll 4
-                for (int c = c_first; c < KK; c += c_step) {
-                    const int i = c / K, j = c - i * K;   // i -> x offset, j -> y offset (transposed window)
-                    const float *pp = pl + j * P + i;
-                    float acc = pp[0] * w00;
-                    acc += pp[1] * w01;
-                    acc += pp[P] * w10;
-                    acc += pp[P + 1] * w11;
-                    ol[(size_t)c * N] = acc;
-                }
+            for (int c = c_first; c < KK; c += c_step) {
+                const int i = c / K, j = c - i * K;   // i -> x offset, j -> y offset (transposed window)
+                const float *pp = pl + j * P + i;
+                float acc = pp[0] * w00;
+                acc += pp[1] * w01;
+                acc += pp[P] * w10;
+                acc += pp[P + 1] * w11;
+                ol[(size_t)c * N] = acc;
             }
         }
     }
-    if (tid == 0) CF_TRACE_AT(3);
 }
 
 CF_DEFINE_TRACE_SETTER(cf_trace_buffer_lookup)
 
-template <int RADIUS, int LEVELS, int QT>
+template <int QT>
+static int launch_lookup_r4l4(const Pyramid &pyr, const float *coords, float *out, int B, int N, cudaStream_t stream) {
+    const size_t smem = (size_t)QT * 401 * sizeof(float);
+    int dev = 0;
+    CF_CUDA(cudaGetDevice(&dev));
+    static bool opt_in[64] = {};
+    if (!opt_in[dev & 63]) {
+        CF_CUDA(cudaFuncSetAttribute(corr_lookup_r4l4_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opt_in[dev & 63] = true;
+    }
+    dim3 grid((unsigned)ceil_div(N, QT), B);
+    // (programmatic dependent launch was tried here: with 12 lookups back to back in a graph it made
+    //  each launch 1.4 us SLOWER on the B200 -- 8.8 vs 7.4 us -- so plain stream order is kept)
+    corr_lookup_r4l4_kernel<QT><<<grid, kLookupThreads, smem, stream>>>(pyr, coords, out, N);
+    CF_LAUNCH_CHECK("corr_lookup_r4l4_kernel");
+    return CF_OK;
+}
+
+template <int QT>
 static int launch_lookup(const Pyramid &pyr, const float *coords, float *out, int B, int N, int levels, int radius,
                          cudaStream_t stream) {
     const int K = 2 * radius + 1, P = K + 1;
@@ -217,13 +256,11 @@ static int launch_lookup(const Pyramid &pyr, const float *coords, float *out, in
     CF_CUDA(cudaGetDevice(&dev));
     static bool opt_in[64] = {};
     if (!opt_in[dev & 63]) {
-        CF_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RADIUS, LEVELS, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CF_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         opt_in[dev & 63] = true;
     }
     dim3 grid((unsigned)ceil_div(N, QT), B);
-    // (programmatic dependent launch was tried here: with 12 lookups back to back in a graph it made
-    //  each launch 1.4 us SLOWER on the B200 -- 8.8 vs 7.4 us -- so plain stream order is kept)
-    corr_lookup_kernel<RADIUS, LEVELS, QT><<<grid, kLookupThreads, smem, stream>>>(pyr, coords, out, N, levels, radius);
+    corr_lookup_kernel<QT><<<grid, kLookupThreads, smem, stream>>>(pyr, coords, out, N, levels, radius);
     CF_LAUNCH_CHECK("corr_lookup_kernel");
     return CF_OK;
 }
@@ -254,9 +291,9 @@ extern "C" int cf_corr_lookup(const float *const *pyramid, const float *coords, 
     // 16 queries per CTA when the problem is small (more CTAs than SMs), else 32 (128-byte stores)
     const bool small = (int64_t)B * ceil_div(N, 32) < 4 * (int64_t)sm_count();
     if (radius == 4 && levels == 4) {
-        return small ? launch_lookup<4, 4, 16>(pyr, coords, out, B, N, levels, radius, stream)
-                     : launch_lookup<4, 4, 32>(pyr, coords, out, B, N, levels, radius, stream);
+        return small ? launch_lookup_r4l4<16>(pyr, coords, out, B, N, stream)
+                     : launch_lookup_r4l4<32>(pyr, coords, out, B, N, stream);
     }
-    return small ? launch_lookup<0, 0, 16>(pyr, coords, out, B, N, levels, radius, stream)
-                 : launch_lookup<0, 0, 32>(pyr, coords, out, B, N, levels, radius, stream);
+    return small ? launch_lookup<16>(pyr, coords, out, B, N, levels, radius, stream)
+                 : launch_lookup<32>(pyr, coords, out, B, N, levels, radius, stream);
 }
