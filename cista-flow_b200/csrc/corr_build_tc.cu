@@ -52,16 +52,21 @@ namespace tc {
 
 constexpr int BM = 128;          // queries per tile (UMMA M)
 constexpr int BK = 32;           // K rows per pipeline stage (4 MMAs of K=8)
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 6;     // ring depth = as many stages of (fmap1 tile + this shape's fmap2 tile) as fit, at most 6
 constexpr int MAX_BN = 256;      // UMMA N limit
 constexpr int BOX_BYTES = 32 * 32 * 4;                 // one TMA box: 32 cols x 32 rows fp32
 constexpr int A_BYTES = (BM / 32) * BOX_BYTES;         // 16 KB
-constexpr int B_BYTES = (MAX_BN / 32) * BOX_BYTES;     // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;         // 48 KB
 constexpr int EPI_BUF_BYTES = 32 * 32 * 4;               // one 32x32 fp32 output box, 128B swizzle
-constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*double buffer*/ * EPI_BUF_BYTES;  // 32 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 192;
+// Epilogue warps per TMEM lane quarter.  2 (eight epilogue warps splitting the tile's work items) was measured
+// SLOWER on the B200 (8 x 60x80: 362 against 334 us; with loads and stores ablated 258 against 238 us): the
+// epilogue is not the critical path, the tf32 MMAs are (operand fetch from shared memory).
+constexpr int EPI_SPLIT = 1;
+constexpr int EPI_WARPS = 4 * EPI_SPLIT;
+constexpr int EPI_BYTES = EPI_WARPS * 2 /*double buffer*/ * EPI_BUF_BYTES;  // 32 KB
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int SMEM_FIXED = EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 32 * (EPI_WARPS + 2);
+constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;  // ~seconds; a stuck pipeline traps instead of hanging the GPU
 
 struct Params {
@@ -71,6 +76,11 @@ struct Params {
     int n_boxes_b; // TMA boxes per stage for the B operand
     int R;         // target rows per tile when pooling is fused (0 = not fused)
     int tiles_m, tiles_n, total_tiles;
+    int tiles_mp;  // pair kernel: pairs of query tiles per batch item (= ceil(tiles_m / 2)); total_tiles counts pairs
+    int stages;      // shared-memory ring depth
+    int stage_bytes; // A_BYTES + n_boxes_b * BOX_BYTES
+    int ablate;    // experiments (CF_TC_FLAGS bits 8-10): 1 = no level-0/1 stores, 2 = no MMAs, 4 = no operand loads, 8 = K-major instruction descriptor
+    int b_half;    // pair kernel: fmap2 boxes per stage and CTA (half of the tile's columns each)
     int h1, w1;    // level-1 map size
     float scale;
     int stream_l0; // 1: level 0 is larger than L2 can hold -> evict-first stores
@@ -118,6 +128,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// (L2 policy hints -- evict_last on these loads, evict_first on the volume stores -- were measured on the B200:
+//  no effect at any shape, so the plain forms are used)
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, int c0, int c1, uint64_t *bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -130,6 +142,38 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, int
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+
+// cta_group::2 variants: the box lands in THIS CTA's shared memory, its bytes complete on the mbarrier at the
+// shared::cluster address `bar_addr` -- the pair leader's `full` barrier (mapa_rank0) for both CTAs of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *m, int c0, int c1, uint32_t bar_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *m, int c0, int c1, int c2, uint32_t bar_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// shared::cluster address of the same shared-memory object in CTA 0 of the cluster
+__device__ __forceinline__ uint32_t mapa_rank0(const void *p) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(0u));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // smem (32 rows x 128 B, 128B swizzle) -> global box {32 cols, 32 rows, 1} of the [B][N][N] volume
@@ -154,6 +198,28 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// pair kernel: arrive on the mbarrier at this offset in every CTA of `mask` once the pair's MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// M = 256 across the CTA pair: each CTA contributes its 128 fmap1 rows and HALF of the fmap2 tile from its own
+// shared memory (same offsets in both CTAs) and receives its 128 x N accumulator rows in its own TMEM
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], tf32 operands, fp32 accumulate
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -189,10 +255,10 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t 
     d |= (uint64_t)1 << 61;                          // layout type 1 = SWIZZLE_128B_BASE32B
     return d;
 }
-// instruction descriptor: D=f32, A=B=tf32, both MN-major, M=128, N=n
-__host__ __device__ inline uint32_t make_idesc_tf32(int n) {
+// instruction descriptor: D=f32, A=B=tf32, both MN-major, M=m (128, or 256 across a CTA pair), N=n
+__host__ __device__ inline uint32_t make_idesc_tf32(int n, int m = BM) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(m >> 4) << 24);
 }
 
 // Debug timeline of CTA 0's first tile (clock64 stamps), read back with cf_debug_tc_timeline().
@@ -201,11 +267,28 @@ __device__ __forceinline__ void stamp(int slot) {
     if (blockIdx.x == 0) g_tc_timeline[slot] = (unsigned long long)clock64();
 }
 
+// experiment builds (-DCF_TRACE, scripts/corr_trace.py): per-CTA, per-tile globaltimer stamps, 16 slots per tile:
+//  0 first load issued, 1 last load issued | 2 accumulator free (MMA), 3..10 stage kb landed, 11 last commit |
+//  12 accumulator ready (epilogue), 13 level-0 chunks issued, 14 epilogue done
+#ifdef CF_TRACE
+#define TC_TRACE(tile_no, slot) do { if ((tile_no) < 15) CF_TRACE_AT(16 + 16 * (tile_no) + (slot)); } while (0)
+#else
+#define TC_TRACE(tile_no, slot) ((void)0)
+#endif
+
 __device__ __forceinline__ void decode_tile(const Params &p, int tile, int &b, int &mb, int &nb) {
     nb = tile % p.tiles_n;
     const int t = tile / p.tiles_n;
     mb = t % p.tiles_m;
     b = t / p.tiles_m;
+}
+// pair kernel: `tile` indexes a pair of vertically adjacent query tiles; CTA `rank` owns query tile 2*pair + rank,
+// which may lie entirely below the volume when tiles_m is odd (its loads are zero-filled, its stores clipped)
+__device__ __forceinline__ void decode_pair_tile(const Params &p, int tile, int rank, int &b, int &mb, int &nb) {
+    nb = tile % p.tiles_n;
+    const int t = tile / p.tiles_n;
+    mb = 2 * (t % p.tiles_mp) + rank;
+    b = t / p.tiles_mp;
 }
 
 template <bool STREAM>
@@ -236,56 +319,100 @@ __device__ __forceinline__ void store_row_chunk(float *dst, const uint32_t (&v)[
     else store_row_chunk_impl<false>(dst, v, scale, nvalid, vec4);
 }
 
+// CL = 1: one CTA per tile.  CL = 2 (tcgen05 cta_group::2): a cluster of two CTAs owns two vertically adjacent
+// query tiles of the same target tile = one 256 x BN UMMA.  Each CTA loads its own 128 fmap1 rows and HALF of the
+// fmap2 columns; the leader (rank 0) issues the MMAs for the pair, each CTA's accumulator rows land in its own TMEM
+// and are drained by its own epilogue.  Per SM and K step this moves and reads (128 + BN/2) x 32 B instead of
+// (128 + BN) x 32 B: the single-CTA tf32 MMA is bound by operand fetch from shared memory (measured: ~50 B/clk,
+// i.e. 181 cycles for 128x160x8 and 243 for 128x256x8 with loads and stores ablated; K-major descriptors on the
+// same bytes change nothing).  Barriers: both producers' bytes complete on the LEADER's `full`; the leader's
+// commits arrive on `empty` / `tfull` of both CTAs; both epilogues arrive on the leader's `tempty`.
+// (A first pair variant only multicast the fmap2 tile to two independent cta_group::1 MMAs: L2 traffic -33 %,
+//  time unchanged -- L2 bandwidth was not the bound.)
+template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *epi = smem + STAGES * STAGE_BYTES;  // [4 warps][2][EPI_BUF_BYTES]
+    const int STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
+    uint8_t *epi = smem + STAGES * STAGE_BYTES;  // [EPI_WARPS][2][EPI_BUF_BYTES]
     uint64_t *bars = reinterpret_cast<uint64_t *>(epi + EPI_BYTES);
-    uint64_t *full = bars, *empty = bars + STAGES;
-    uint64_t *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    uint64_t *full = bars, *empty = bars + MAX_STAGES;
+    uint64_t *tfull = bars + 2 * MAX_STAGES, *tempty = bars + 2 * MAX_STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = p.D / BK;
+    const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
+    const int first_tile = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
     if (threadIdx.x == 0) stamp(0);
 
-    if (warp == 4 && lane == 0) {
+    if (warp == PRODUCER_WARP && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         tma_prefetch_desc(&tmap_c);
     }
-    if (warp == 5) {
+    if (warp == MMA_WARP) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 32 * EPI_WARPS * CL); }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, 512);
+        if (CL == 2) tmem_alloc_2sm(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised (and its TMEM allocated) before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) stamp(1);
 
-    if (warp == 4) {
+    if (warp == PRODUCER_WARP) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)(BM / 32 + p.n_boxes_b) * BOX_BYTES;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            // pair kernel: the leader's barrier counts the bytes of BOTH CTAs' boxes
+            const uint32_t tx_bytes = (uint32_t)(CL * (BM / 32 + (CL == 2 ? p.b_half : p.n_boxes_b))) * BOX_BYTES;
+            const int jr = CL == 2 ? rank * (p.BN_mma / 2) : 0;  // first fmap2 column of this CTA inside the tile
+            int tile_no = 0;
+            for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
                 int b, mb, nb;
-                decode_tile(p, tile, b, mb, nb);
+                if (CL == 2) decode_pair_tile(p, tile, rank, b, mb, nb);
+                else decode_tile(p, tile, b, mb, nb);
                 const int i0 = mb * BM, j0 = nb * p.BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
+                    if (kb == 0) TC_TRACE(tile_no, 0);
+                    if (kb == kblocks - 1) TC_TRACE(tile_no, 1);
                     uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + A_BYTES;
-                    mbar_expect_tx(&full[stage], tx_bytes);
+                    if (p.ablate & 4) {
+                        if (rank == 0) mbar_arrive(&full[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     const int krow = b * p.D + kb * BK;
+                    if (CL == 2) {
+                        if (rank == 0) mbar_expect_tx(&full[stage], tx_bytes);
+                        const uint32_t lead_full = mapa_rank0(&full[stage]);
+                        if (p.atoms3d) {
+                            tma_load_3d_2sm(sa, &tmap_a, 0, krow, i0 >> 5, lead_full);
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < BM / 32; ++a) tma_load_2d_2sm(sa + a * BOX_BYTES, &tmap_a, i0 + 32 * a, krow, lead_full);
+                        }
+                        if (p.b3d) {
+                            tma_load_3d_2sm(sb, &tmap_b, 0, krow, (j0 + jr) >> 5, lead_full);
+                        } else {
+                            for (int a = 0; a < p.b_half; ++a) tma_load_2d_2sm(sb + a * BOX_BYTES, &tmap_b, j0 + jr + 32 * a, krow, lead_full);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    mbar_expect_tx(&full[stage], tx_bytes);
                     if (p.atoms3d) {
                         tma_load_3d(sa, &tmap_a, 0, krow, i0 >> 5, &full[stage]);
                     } else {
@@ -297,56 +424,73 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     } else {
                         for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOX_BYTES, &tmap_b, j0 + 32 * a, krow, &full[stage]);
                     }
-                    if (tile == (int)blockIdx.x && kb == 0) stamp(2);
+                    if (tile == first_tile && kb == 0) stamp(2);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == MMA_WARP) {
         // -------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            const uint32_t idesc = make_idesc_tf32(p.BN_mma);
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            uint32_t idesc = make_idesc_tf32(p.BN_mma, CL * BM);
+            if (p.ablate & 8) idesc &= ~((1u << 15) | (1u << 16));  // experiment: K-major reads of the same bytes (garbage results)
+            int tile_no = 0;
+            for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
                 tc_fence_after();
+                TC_TRACE(tile_no, 2);
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    if (tile == (int)blockIdx.x && kb < 16) stamp(3 + kb);
+                    if (tile == first_tile && kb < 16) stamp(3 + kb);
+                    if (kb < 8) TC_TRACE(tile_no, 3 + kb);
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
-                    for (int kk = 0; kk < BK / 8; ++kk)
-                        umma_tf32(d_tmem, make_desc_mn_sw128(sa + kk * 1024), make_desc_mn_sw128(sb + kk * 1024), idesc,
-                                  (uint32_t)((kb | kk) != 0));
-                    umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+                    for (int kk = 0; kk < BK / 8; ++kk) {
+                        if (p.ablate & 2) continue;
+                        const uint64_t da = make_desc_mn_sw128(sa + kk * 1024), db = make_desc_mn_sw128(sb + kk * 1024);
+                        if (CL == 2) umma_tf32_2sm(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
+                        else umma_tf32(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
+                    }
+                    // frees the smem slot once these MMAs have read it (pair kernel: in both CTAs)
+                    if (CL == 2) umma_commit_2sm(&empty[stage], (uint16_t)3);
+                    else umma_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
-                if (tile == (int)blockIdx.x) stamp(19);
+                if (CL == 2) umma_commit_2sm(&tfull[acc], (uint16_t)3);  // accumulator complete -> both epilogues
+                else umma_commit(&tfull[acc]);
+                if (tile == first_tile) stamp(19);
+                TC_TRACE(tile_no, 11);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
         }
     } else {
         // ---------------------------------------------------------------- epilogue
+        // warp <-> TMEM lane quarter warp % 4 (a warp may only read those lanes); with EPI_SPLIT > 1 the warps of a
+        // quarter take the tile's work items (32-column level-0 chunks, 32-column pooling strips) in turn
         int acc = 0;
         uint32_t acc_phase = 0, chunk_count = 0;
-        const int row = 32 * warp + lane;
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = 32 * quarter + lane;
         const bool vec4_l0 = (p.N % 4) == 0 && (p.w % 4) == 0;
         const bool vec4_l1 = (p.w1 % 4) == 0;
         uint8_t *my_epi = epi + warp * 2 * EPI_BUF_BYTES;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int tile_no = 0;
+        for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
             int b, mb, nb;
-            decode_tile(p, tile, b, mb, nb);
+            if (CL == 2) decode_pair_tile(p, tile, rank, b, mb, nb);
+            else decode_tile(p, tile, b, mb, nb);
             const int i = mb * BM + row;
             const bool row_ok = i < p.N;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            if (tile == (int)blockIdx.x && threadIdx.x == 0) stamp(20);
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)acc * MAX_BN;
+            if (tile == first_tile && threadIdx.x == 0) stamp(20);
+            if (threadIdx.x == 0) TC_TRACE(tile_no, 12);
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)acc * MAX_BN;
             const int j0 = nb * p.BN;
             const int bn_valid = min(p.BN, p.N - j0);  // accumulator column c <-> target index j0 + c
             // ---- level 0: TMEM -> registers (x scale) -> swizzled smem box -> TMA bulk store.
@@ -354,7 +498,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // (measured: 18k cycles per tile); the TMA writes whole 128-byte lines instead.
             if (bn_valid >= 32) {
                 const int nchunks = (bn_valid + 31) / 32;
-                for (int ci = 0; ci < nchunks; ++ci) {
+                for (int ci = half; ci < nchunks; ci += EPI_SPLIT) {
                     const int c0 = min(ci * 32, bn_valid - 32);  // last chunk overlaps its neighbour (same values)
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
@@ -372,32 +516,35 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) {
-                        tma_store_3d(&tmap_c, buf, j0 + c0, mb * BM + 32 * warp, b);
+                    if (lane == 0 && mb * BM + 32 * quarter < p.N && !(p.ablate & 1)) {  // (rows below the volume: nothing to store)
+                        tma_store_3d(&tmap_c, buf, j0 + c0, mb * BM + 32 * quarter, b);
                         tma_store_commit();
                     }
                     ++chunk_count;
                 }
-            } else {
+            } else if (half == 0) {
                 float *l0row = p.l0 + ((size_t)b * p.N + (row_ok ? i : 0)) * p.N;
                 uint32_t v[32];
                 tmem_ld32(taddr, v);
                 tmem_ld_wait();
                 if (row_ok && bn_valid > 0) store_row_chunk(l0row + j0, v, p.scale, bn_valid, vec4_l0 && (bn_valid % 4 == 0), false);
             }
+            if (threadIdx.x == 0) TC_TRACE(tile_no, 13);
             // ---- level 1: 2x2 means straight from the accumulator rows
             if (p.R != 0) {
                 const int y0 = nb * p.R;
                 float *l1map = p.l1 + ((size_t)b * p.N + (row_ok ? i : 0)) * p.h1 * p.w1;
+                int item = EPI_SPLIT - 1;  // an odd chunk count leaves the last warp of a quarter one item short: it starts here
                 for (int pr = 0; pr < p.R; pr += 2) {
                     const int y = y0 + pr;
                     if (y + 1 >= p.h) break;  // warp-uniform
                     for (int xc = 0; xc < p.w; xc += 32) {
+                        if (((item++) % EPI_SPLIT) != half) continue;
                         uint32_t ra[32], rc[32];
                         tmem_ld32(taddr + pr * p.w + xc, ra);
                         tmem_ld32(taddr + (pr + 1) * p.w + xc, rc);
                         tmem_ld_wait();
-                        if (row_ok) {
+                        if (row_ok && !(p.ablate & 1)) {
                             // ATen avg_pool2d: ((a + b) + c) + d, then / 4, on the stored (scaled) values
                             float *dst = l1map + (size_t)(y >> 1) * p.w1 + (xc >> 1);
                             const int npool = min(16, p.w1 - (xc >> 1));
@@ -424,18 +571,23 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty[acc]);
-            if (tile == (int)blockIdx.x && threadIdx.x == 0) stamp(21);
+            if (CL == 2) mbar_arrive_cluster(mapa_rank0(&tempty[acc]));
+            else mbar_arrive(&tempty[acc]);
+            if (tile == first_tile && threadIdx.x == 0) stamp(21);
+            if (threadIdx.x == 0) TC_TRACE(tile_no, 14);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
     }
-    if (warp < 4 && lane == 0) tma_store_wait_all();  // bulk stores must drain before the CTA's smem goes away
+    if (warp < EPI_WARPS && lane == 0) tma_store_wait_all();  // bulk stores must drain before the CTA's smem goes away
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    __syncwarp();
+    if (CL == 2) cluster_sync_all();  // the peer may still commit onto this CTA's barriers until its own loop ends
+    if (warp == MMA_WARP) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (CL == 2) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
     if (threadIdx.x == 0) stamp(22);
 }
@@ -451,6 +603,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // operand and stage (atoms3d / b3d above) instead of 9-12 per-atom boxes -- a single thread issues a
 // cp.async.bulk.tensor only about every 100 cycles, which was the main-loop bound (368 -> 327 us).
 // Next lever (not done): cta_group::2 pairs (M = 256 across two SMs, each loading half of the fmap2 tile).
+
+CF_DEFINE_TRACE_SETTER(cf_trace_buffer_corr)
 
 // ---- host side --------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -563,6 +717,24 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     const CUtensorMapDataType dt = (flags & 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
     p.atoms3d = (N % 32 == 0) && !(flags & 16);
     p.b3d = p.atoms3d && (p.BN % 32 == 0 || p.tiles_n == 1);
+    // pairs of query tiles sharing their fmap2 tile through TMA multicast (flags bit5 = off)
+    p.stage_bytes = A_BYTES + p.n_boxes_b * BOX_BYTES;
+    p.stages = (SMEM_LIMIT - SMEM_FIXED) / p.stage_bytes;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    // pairs of query tiles as one 256-row UMMA across two CTAs: measured slower than one CTA per tile on the B200
+    // (8 x 60x80: 359 against 322 us, see the kernel's header), so only on request (flags bit6)
+    const bool pair = (flags & 64) && p.tiles_m >= 2;
+    p.ablate = (flags >> 8) & 15;
+    p.tiles_mp = (int)ceil_div(p.tiles_m, 2);
+    p.b_half = (int)ceil_div(p.BN_mma / 2, 32);
+    if (pair) {
+        p.total_tiles = B * p.tiles_mp * p.tiles_n;
+        p.b3d = p.b3d && (p.BN_mma / 2) % 32 == 0;
+        p.stage_bytes = A_BYTES + p.b_half * BOX_BYTES;
+        p.stages = (SMEM_LIMIT - SMEM_FIXED) / p.stage_bytes;
+        if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    }
+    const int smem_bytes = p.stages * p.stage_bytes + SMEM_FIXED;
     CUtensorMap ta, tb, tcm;
     if (p.atoms3d) {
         if (int rc = make_fmap_tmap3(&ta, a, B, D, N, dt, BK, BM / 32)) return rc;
@@ -570,7 +742,7 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         if (int rc = make_fmap_tmap(&ta, a, B, D, N, dt)) return rc;
     }
     if (p.b3d) {
-        if (int rc = make_fmap_tmap3(&tb, bm, B, D, N, dt, BK, p.n_boxes_b)) return rc;
+        if (int rc = make_fmap_tmap3(&tb, bm, B, D, N, dt, BK, pair ? p.b_half : p.n_boxes_b)) return rc;
     } else {
         if (int rc = make_fmap_tmap(&tb, bm, B, D, N, dt)) return rc;
     }
@@ -580,12 +752,31 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     CF_CUDA(cudaGetDevice(&dev));
     static bool opt_in[64] = {};
     if (!opt_in[dev & 63]) {
-        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         opt_in[dev & 63] = true;
     }
     const int sms = sm_count();
+    if (pair) {
+        const int clusters = p.total_tiles < sms / 2 ? p.total_tiles : sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * clusters));
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CF_CUDA(cudaLaunchKernelEx(&cfg, corr_tc_kernel<2>, ta, tb, tcm, p));
+        CF_LAUNCH_CHECK("corr_tc_kernel<pair>");
+        return CF_OK;
+    }
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-    corr_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, tcm, p);
+    corr_tc_kernel<1><<<grid, THREADS, smem_bytes, stream>>>(ta, tb, tcm, p);
     CF_LAUNCH_CHECK("corr_tc_kernel");
     return CF_OK;
 }

@@ -455,6 +455,38 @@ def test_corr_golden(golden, cuda_device, precision, tol):
     assert tuple(vol.shape) == (1, 16, 24, 1, 16, 24)
 
 
+def test_corr_pair_kernel_subprocess(cuda_device):
+    """The cta_group::2 variant of the tensor-core correlation (CF_TC_FLAGS bit6, read once per process, hence the
+    subprocess): 256-row UMMAs across a CTA pair.  Checked against the fp32 SIMT kernel at an even tile count
+    (24x32, 3-D operand boxes), an odd one (36x44: 13 query tiles -> one dummy tile, per-atom boxes, N/2 not on
+    a box boundary) and 60x80 (BN = 160: half tiles of 2.5 boxes)."""
+    import os
+    import subprocess
+    import sys
+    code = """
+import numpy as np, torch
+import cistaflow_b200 as cf
+from cistaflow_b200 import synth, _lib
+dev = torch.device('cuda', 0)
+for (H, W, B) in ((192, 256, 2), (288, 352, 2), (480, 640, 1)):
+    f1, f2, _ = synth.corr_inputs(B, H, W, 5)
+    a, b = torch.from_numpy(f1).to(dev), torch.from_numpy(f2).to(dev)
+    ref = cf.build_pyramid(a, b, 4, precision='fp32')
+    cf.build_pyramid(a, b, 2, precision='tf32')   # two levels: the fused kernel is the only launch
+    assert _lib.load().cf_last_kernel().decode() == 'corr_tc_kernel<pair>', _lib.load().cf_last_kernel()
+    got = cf.build_pyramid(a, b, 4, precision='tf32')
+    for l in range(4):
+        r = ref[l].float(); g = got[l].float()
+        err = (g - r).abs().max().item() / r.abs().max().item()
+        assert err <= 1e-3, (H, W, l, err)
+print('PAIR_OK')
+"""
+    env = dict(os.environ, CF_TC_FLAGS="64")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert res.returncode == 0 and "PAIR_OK" in res.stdout, res.stdout + res.stderr
+
+
 def test_corr_golden_odd_sizes(golden, cuda_device):
     """15x20 maps, 3 levels, radius 3: avg_pool floors, runtime-radius lookup kernel."""
     g = golden("corr")
