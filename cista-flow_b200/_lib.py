@@ -41,6 +41,8 @@ SYMBOLS = {
     "cf_voxel_bin_packed": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp, _vp, _sz, _vp]),
     "cf_warp": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "cf_warp_frame_and_codes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "cf_flow_any": (_i, [_vp, _i64, _vp, _vp]),
+    "cf_warp_frame_and_codes_gated": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "cf_warp_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "cf_voxel_flow_warp_workspace_bytes": (_sz, [_i, _i, _i]),
     "cf_voxel_flow_warp": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

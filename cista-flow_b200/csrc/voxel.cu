@@ -30,6 +30,11 @@
 //                  events of each pixel in event order, then one thread per
 //                  pixel walks its run bin by bin with un-contracted IEEE
 //                  adds (__fadd_rn / fp64 add + round for the NumPy flavour).
+// Measured and dropped (round 1): taking the std statistics out of the scatter itself -- returning atomics
+// (ATOMG instead of RED) give each add's previous value o, and sum f(o + w) - f(o) telescopes to the final
+// grid's sum / sum of squares / non-zero count, so the separate statistics pass disappears.  Correct (all parity
+// tests green) but 1.4-4x SLOWER end to end on the B200 (8x180x240: 24.4 against 16.6 us; 64x260x346: 543 against
+// 132 us): returning atomics cost far more than the pass over the L2-resident grid they save.
 // Time normalisation is fp64 with the reference's operation order
 // (mul, then div) in both modes, so bin assignment is identical.
 #include <cooperative_groups.h>
@@ -558,6 +563,8 @@ voxel_normalise_kernel(const float *in, float *out /* may alias in */, int64_t c
         const float r = (v - a) * inv;
         return (mode == CF_PRE_STD && v == 0.f) ? 0.f : r;
     };
+    // in place, std mode: zero cells stay zero (event_process.py:207-210) -- an all-zero float4 is not rewritten
+    const bool skip_zero = (in == out) && mode == CF_PRE_STD;
     if (vec) {
         for (int64_t i = i0; i < e4; i += 4 * kStatThreads) {
             if (i != i0) {
@@ -570,7 +577,10 @@ voxel_normalise_kernel(const float *in, float *out /* may alias in */, int64_t c
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int64_t j = i + (int64_t)u * kStatThreads;
-                if (j < e4) o4[j] = make_float4(norm(q[u].x), norm(q[u].y), norm(q[u].z), norm(q[u].w));
+                if (j < e4) {
+                    if (skip_zero && q[u].x == 0.f && q[u].y == 0.f && q[u].z == 0.f && q[u].w == 0.f) continue;
+                    o4[j] = make_float4(norm(q[u].x), norm(q[u].y), norm(q[u].z), norm(q[u].w));
+                }
             }
         }
     } else {

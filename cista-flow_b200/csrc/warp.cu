@@ -23,32 +23,46 @@ namespace cf {
 
 // implemented in warp_tma.cu: CF_OK / error, or 1 when the TMA-staged path does not apply
 int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const float *flow, int fH, int fW, float sign,
-                    int B, cudaStream_t stream);
+                    int B, const int *gate, cudaStream_t stream);
 
 static int launch_staged(const WarpJob &ji, bool with_image, const WarpJob &jz, const float *flow, int fH, int fW,
-                         float sign, int B, cudaStream_t stream) {
-    return launch_warp_tma(ji, with_image, jz, flow, fH, fW, sign, B, stream);
+                         float sign, int B, const int *gate, cudaStream_t stream) {
+    return launch_warp_tma(ji, with_image, jz, flow, fH, fW, sign, B, gate, stream);
+}
+
+// flag[0] = 1 iff any element of flow is non-zero (NaN counts, -0.0 does not: torch.Tensor.any()).  flag is zeroed
+// by the host side before the launch; CTAs that see a non-zero element store 1 (same value from everyone: no atomic).
+__global__ void __launch_bounds__(256) flow_any_kernel(const float *__restrict__ flow, int64_t n, int *__restrict__ flag) {
+    bool any = false;
+    const int64_t n4 = n >> 2;
+    const float4 *f4 = reinterpret_cast<const float4 *>(flow);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(f4 + i);
+        any = any || !(v.x == 0.f) || !(v.y == 0.f) || !(v.z == 0.f) || !(v.w == 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) any = any || !(flow[(n4 << 2) + threadIdx.x] == 0.f);
+    if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;
 }
 
 template <int CPT>
 __global__ void __launch_bounds__(256, 4) warp_gather_kernel(WarpJob j, const float *__restrict__ flow,
                                                           int fH, int fW, float sign) {
-    run_job<CPT>(j, flow, fH, fW, sign, blockIdx.x, blockIdx.y, blockIdx.z);
+    run_job<CPT>(j, flow, fH, fW, sign, blockIdx.x, blockIdx.y, blockIdx.z, nullptr);
 }
 
 // image (CPT=1 per thread, few channels) + codes (CPT=8, 32 channels per thread) in one launch:
 // blockIdx.x < img.blocks_x*img.groups -> image part, the rest -> codes part.
 __global__ void __launch_bounds__(256, 4) warp_frame_and_codes_kernel(WarpJob ji, WarpJob jz,
                                                                    const float *__restrict__ flow,
-                                                                   int fH, int fW, float sign) {
+                                                                   int fH, int fW, float sign, const int *__restrict__ gate) {
     const int b = blockIdx.y;
     int blk = blockIdx.x;
     const int n_img = ji.blocks_x * ji.groups;
     if (blk < n_img) {
-        run_job<1>(ji, flow, fH, fW, sign, blk % ji.blocks_x, blk / ji.blocks_x, b);
+        run_job<1>(ji, flow, fH, fW, sign, blk % ji.blocks_x, blk / ji.blocks_x, b, gate);
     } else {
         blk -= n_img;
-        run_job<8>(jz, flow, fH, fW, sign, blk % jz.blocks_x, blk / jz.blocks_x, b);
+        run_job<8>(jz, flow, fH, fW, sign, blk % jz.blocks_x, blk / jz.blocks_x, b, gate);
     }
 }
 
@@ -90,7 +104,7 @@ extern "C" int cf_warp(const float *img, const float *flow, float *out, int B, i
     if (int rc = make_job(j, img, out, C, H, W, flowH, flowW, cpt)) return rc;
     CF_REQUIRE(j.groups <= 65535, CF_ERR_INVALID_ARG, "cf_warp: too many channels");
     if (C >= 8) {  // multi-channel tensors: TMA-staged kernel when the shape allows it
-        const int rc = launch_staged(j, false, j, flow, flowH, flowW, sign, B, stream);
+        const int rc = launch_staged(j, false, j, flow, flowH, flowW, sign, B, nullptr, stream);
         if (rc != 1) return rc;
     }
     dim3 grid(j.blocks_x, j.groups, B);
@@ -101,9 +115,32 @@ extern "C" int cf_warp(const float *img, const float *flow, float *out, int B, i
     return CF_OK;
 }
 
+extern "C" int cf_flow_any(const float *flow, int64_t n, int *flag, cf_stream_t stream_) {
+    using namespace cf;
+    if (int rc = check_device()) return rc;
+    CF_REQUIRE(flag && (flow || n == 0), CF_ERR_NULL, "cf_flow_any: null pointer");
+    CF_REQUIRE(n >= 0, CF_ERR_INVALID_ARG, "cf_flow_any: negative size");
+    CF_REQUIRE(n == 0 || aligned16(flow), CF_ERR_ALIGN, "cf_flow_any: flow not 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CF_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
+    if (n == 0) return CF_OK;
+    int64_t blocks = ceil_div(n, 256 * 4 * 4);  // ~4 float4 per thread
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    flow_any_kernel<<<(unsigned)blocks, 256, 0, stream>>>(flow, n, flag);
+    CF_LAUNCH_CHECK("flow_any_kernel");
+    return CF_OK;
+}
+
 extern "C" int cf_warp_frame_and_codes(const float *img, const float *codes, const float *flow,
                                        float *img_out, float *codes_out, int B, int Ci, int Cz,
                                        int H, int W, float sign, cf_stream_t stream_) {
+    return cf_warp_frame_and_codes_gated(img, codes, flow, img_out, codes_out, B, Ci, Cz, H, W, sign, nullptr, stream_);
+}
+
+extern "C" int cf_warp_frame_and_codes_gated(const float *img, const float *codes, const float *flow,
+                                             float *img_out, float *codes_out, int B, int Ci, int Cz,
+                                             int H, int W, float sign, const int *gate, cf_stream_t stream_) {
     using namespace cf;
     if (int rc = check_device()) return rc;
     CF_REQUIRE(img && codes && flow && img_out && codes_out, CF_ERR_NULL, "cf_warp_frame_and_codes: null pointer");
@@ -117,11 +154,11 @@ extern "C" int cf_warp_frame_and_codes(const float *img, const float *codes, con
     if (int rc = make_job(ji, img, img_out, Ci, H, W, H, W, 1)) return rc;
     if (int rc = make_job(jz, codes, codes_out, Cz, H / 2, W / 2, H, W, 8)) return rc;
     {
-        const int rc = launch_staged(ji, true, jz, flow, H, W, sign, B, stream);
+        const int rc = launch_staged(ji, true, jz, flow, H, W, sign, B, gate, stream);
         if (rc != 1) return rc;
     }
     dim3 grid(ji.blocks_x * ji.groups + jz.blocks_x * jz.groups, B);
-    warp_frame_and_codes_kernel<<<grid, 256, 0, stream>>>(ji, jz, flow, H, W, sign);
+    warp_frame_and_codes_kernel<<<grid, 256, 0, stream>>>(ji, jz, flow, H, W, sign, gate);
     CF_LAUNCH_CHECK("warp_frame_and_codes_kernel");
     return CF_OK;
 }

@@ -78,6 +78,19 @@ __device__ __forceinline__ Taps make_taps(float u, float v, int x, int y, int H,
     return t;
 }
 
+// Taps that reproduce the input pixel (weights 1, 0, 0, 0): what the reference's `if not flow_final.any()` branch
+// returns (e2v/e2v_model.py:184-185).  Used when the device-side gate says the flow is all zero -- a zero flow is
+// NOT the identity under the reference's 2*(x/W-0.5) normalisation, hence the explicit branch.
+__device__ __forceinline__ Taps identity_taps(int x, int y, int W) {
+    Taps t;
+    t.o00 = t.o01 = t.o10 = t.o11 = y * W + x;
+    t.w00 = 1.f;
+    t.w01 = t.w10 = t.w11 = 0.f;
+    return t;
+}
+// gate == nullptr: always warp; else *gate == 0 (written by cf_flow_any) means "flow is all zero": copy
+__device__ __forceinline__ bool gate_closed(const int *__restrict__ gate) { return gate != nullptr && __ldg(gate) == 0; }
+
 // One thread = one output pixel x CPT channels.
 template <int CPT>
 __device__ __forceinline__ void warp_pixel(const float *__restrict__ img_b, float *__restrict__ out_b,
@@ -120,14 +133,19 @@ constexpr int kTileW = 32, kTileH = 8;
 
 template <int CPT>
 __device__ __forceinline__ void run_job(const WarpJob &j, const float *__restrict__ flow,
-                                        int fH, int fW, float sign, int tile, int group, int b) {
+                                        int fH, int fW, float sign, int tile, int group, int b, const int *__restrict__ gate) {
     const int ty = tile / j.tiles_x, tx = tile - ty * j.tiles_x;
     const int x = tx * kTileW + (threadIdx.x & 31), y = ty * kTileH + (threadIdx.x >> 5);
     if (x >= j.W || y >= j.H) return;
     const int p = y * j.W + x;
     const float *fb = flow + (size_t)b * 2 * fH * fW;
-    const float2 uv = flow_at(fb, x, y, j.W, fH, fW, j.half != 0, j.sy, j.sx);
-    const Taps t = make_taps(uv.x, uv.y, x, y, j.H, j.W, sign);
+    Taps t;
+    if (gate_closed(gate)) {
+        t = identity_taps(x, y, j.W);
+    } else {
+        const float2 uv = flow_at(fb, x, y, j.W, fH, fW, j.half != 0, j.sy, j.sx);
+        t = make_taps(uv.x, uv.y, x, y, j.H, j.W, sign);
+    }
     const size_t plane = (size_t)j.H * j.W;
     const float *img_b = j.img + (size_t)b * j.C * plane;
     float *out_b = j.out + (size_t)b * j.C * plane;

@@ -47,8 +47,9 @@ constexpr int CH_PER_CTA = 32;           // channel group of one CTA (4 stages o
 
 __global__ void __launch_bounds__(256, 3)
 warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_blocks, WarpJob jz, int tiles_x, int tiles,
-                int groups, const float *__restrict__ flow, int fH, int fW, float sign) {
+                int groups, const float *__restrict__ flow, int fH, int fW, float sign, const int *__restrict__ gate) {
     using namespace wt;
+    const bool identity = gate_closed(gate);  // device-side `not flow_final.any()` (e2v_model.py:184): copy
     const int b = blockIdx.y;
     int blk = blockIdx.x;
     const int n_codes_blocks = tiles * groups;
@@ -75,7 +76,8 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_
         }
         Taps t[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) t[k] = make_taps(fu[k], fv[k], xc, min(yy[k], Hi - 1), Hi, Wi, sign);
+        for (int k = 0; k < 4; ++k)
+            t[k] = identity ? identity_taps(xc, min(yy[k], Hi - 1), Wi) : make_taps(fu[k], fv[k], xc, min(yy[k], Hi - 1), Hi, Wi, sign);
         for (int c = 0; c < ji.C; ++c) {
             const float *src = ji.img + ((size_t)b * ji.C + c) * hw;
             float *dst = ji.out + ((size_t)b * ji.C + c) * hw;
@@ -121,8 +123,12 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_
         const int y = ty * TH + warp + 8 * k;
         live[k] = x < W && y < H;
         if (live[k]) {
-            const float2 uv = flow_at(fb, x, y, W, fH, fW, jz.half != 0, jz.sy, jz.sx);
-            taps[k] = make_taps(uv.x, uv.y, x, y, H, W, sign);
+            if (identity) {
+                taps[k] = identity_taps(x, y, W);
+            } else {
+                const float2 uv = flow_at(fb, x, y, W, fH, fW, jz.half != 0, jz.sy, jz.sx);
+                taps[k] = make_taps(uv.x, uv.y, x, y, H, W, sign);
+            }
             y0a[k] = taps[k].o00 / W;
             x0a[k] = taps[k].o00 - y0a[k] * W;
             mnx = min(mnx, x0a[k]); mny = min(mny, y0a[k]);
@@ -227,7 +233,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_
 }
 
 int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const float *flow, int fH, int fW, float sign,
-                    int B, cudaStream_t stream) {
+                    int B, const int *gate, cudaStream_t stream) {
     using namespace wt;
     static const char *env = getenv("CF_WARP_PATH");  // experiments: "direct" forces the plain gather
     const bool disabled = env && !strcmp(env, "direct");
@@ -255,7 +261,7 @@ int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const
     const int groups = (int)ceil_div(jz.C, CH_PER_CTA);
     const int n_img = with_image ? (int)(ceil_div(ji.W, 32) * ceil_div(ji.H, 32)) : 0;
     dim3 grid((unsigned)(n_img + tiles * groups), (unsigned)B);
-    warp_tma_kernel<<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, n_img, jz, tiles_x, tiles, groups, flow, fH, fW, sign);
+    warp_tma_kernel<<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, n_img, jz, tiles_x, tiles, groups, flow, fH, fW, sign, gate);
     CF_LAUNCH_CHECK("warp_tma_kernel");
     return CF_OK;
 }

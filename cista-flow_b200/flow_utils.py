@@ -85,10 +85,30 @@ def _warp_forward(img: torch.Tensor, flow: torch.Tensor, sign: float, out: torch
     return out
 
 
+def flow_any(flow: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``flow.any()`` as a device-side int32 flag (1 = some element is non-zero), no host synchronisation.
+    The reference reads this predicate on the host in every frame (e2v/e2v_model.py:184, 236)."""
+    flow = _prep(flow, "flow")
+    if out is None:
+        out = torch.empty(1, dtype=torch.int32, device=flow.device)
+    assert out.dtype == torch.int32 and out.numel() >= 1 and out.device == flow.device
+    lib = _lib.load()
+    with torch.cuda.device(flow.device):
+        rc = lib.cf_flow_any(flow.data_ptr(), flow.numel(), out.data_ptr(), _lib.stream_ptr(flow.device))
+    _lib.check(rc, "cf_flow_any")
+    return out
+
+
 def warp_frame_and_codes(img: torch.Tensor, codes: torch.Tensor, flow: torch.Tensor, mode: str = "forward",
-                         out: tuple[torch.Tensor, torch.Tensor] | None = None):
+                         out: tuple[torch.Tensor, torch.Tensor] | None = None, skip_zero_flow: bool = False,
+                         gate: torch.Tensor | None = None):
     """One launch for ``e2v/e2v_model.py:188-191``: returns (warped image, warped codes).
-    img [B,Ci,H,W], codes [B,Cz,H//2,W//2], flow [B,2,H,W]."""
+    img [B,Ci,H,W], codes [B,Cz,H//2,W//2], flow [B,2,H,W].
+
+    ``skip_zero_flow=True`` reproduces the whole branch of ``e2v_model.py:184-191`` -- when the flow is all zero
+    the reference skips the warp and keeps ``rec_img0`` / ``states[1]`` -- with the predicate evaluated on the
+    device (``cf_flow_any`` + a gated kernel that copies instead of warping): no ``.any()`` read-back, so the frame
+    step stays asynchronous and can be captured in a CUDA graph.  ``gate`` passes a flag computed earlier."""
     img, codes, flow = _prep(img, "img"), _prep(codes, "codes"), _prep(flow, "flow")
     B, Ci, H, W = img.shape
     assert flow.shape == (B, 2, H, W), "flow must be [B,2,H,W] at the image resolution"
@@ -101,11 +121,15 @@ def warp_frame_and_codes(img: torch.Tensor, codes: torch.Tensor, flow: torch.Ten
         for o, ref in ((img_out, img), (codes_out, codes)):
             assert o.shape == ref.shape and o.dtype == torch.float32 and o.is_contiguous() and o.device == ref.device
     sign = -1.0 if mode == "forward" else 1.0
+    if skip_zero_flow and gate is None:
+        gate = flow_any(flow)
+    if gate is not None:
+        assert gate.dtype == torch.int32 and gate.device == img.device
     lib = _lib.load()
     with torch.cuda.device(img.device):
-        rc = lib.cf_warp_frame_and_codes(img.data_ptr(), codes.data_ptr(), flow.data_ptr(), img_out.data_ptr(),
-                                         codes_out.data_ptr(), B, Ci, codes.shape[1], H, W, sign,
-                                         _lib.stream_ptr(img.device))
+        rc = lib.cf_warp_frame_and_codes_gated(img.data_ptr(), codes.data_ptr(), flow.data_ptr(), img_out.data_ptr(),
+                                               codes_out.data_ptr(), B, Ci, codes.shape[1], H, W, sign,
+                                               _lib.ptr(gate), _lib.stream_ptr(img.device))
     _lib.check(rc, "cf_warp_frame_and_codes")
     return img_out, codes_out
 
@@ -151,6 +175,6 @@ class FrameWarp(object):
         height, width = I.shape[-2:]
         return self.get_flowWarp_module(width, height)(I, flow)
 
-    def warp_frame_and_codes(self, I, Z, flow):
+    def warp_frame_and_codes(self, I, Z, flow, skip_zero_flow: bool = False):
         """Fused image + codes step (extension; not in the reference)."""
-        return warp_frame_and_codes(I, Z, flow, self.mode)
+        return warp_frame_and_codes(I, Z, flow, self.mode, skip_zero_flow=skip_zero_flow)

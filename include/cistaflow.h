@@ -162,6 +162,19 @@ CF_API int cf_warp_frame_and_codes(const float *img, const float *codes, const f
                             float *img_out, float *codes_out, int B, int Ci, int Cz,
                             int H, int W, float sign, cf_stream_t stream);
 
+/* Device-side form of `if not flow_final.any(): warped_I = rec_img0 (states untouched)`
+ * (e2v/e2v_model.py:184-191, 236-243): the reference reads the predicate back to
+ * the host -- a synchronisation in every frame, and the reason the frame step cannot be captured in a CUDA graph.
+ *   cf_flow_any       flag[0] = 1 iff any of the n floats of flow is non-zero (NaN counts, -0.0 does not:
+ *                     torch.Tensor.any()); flag is a device int, zeroed and written on `stream`.
+ *   ..._gated         as cf_warp_frame_and_codes, but when gate != NULL and *gate == 0 the outputs are COPIES of
+ *                     img / codes (what the reference's branch returns; a zero flow is not the identity under its
+ *                     grid normalisation).  gate == NULL: always warp.  No host synchronisation, graph-capturable. */
+CF_API int cf_flow_any(const float *flow, int64_t n, int *flag, cf_stream_t stream);
+CF_API int cf_warp_frame_and_codes_gated(const float *img, const float *codes, const float *flow,
+                                  float *img_out, float *codes_out, int B, int Ci, int Cz,
+                                  int H, int W, float sign, const int *gate, cf_stream_t stream);
+
 /* Adjoint of cf_warp: what autograd runs through forwardWarp / backWarp in
  * training (loss.py:147,336,398; train.py:208-232).  grad_out [B,C,H,W];
  *   grad_img  [B,C,H,W]           <- bilinear SPLAT of grad_out into the 4 taps (may be NULL)

@@ -403,6 +403,52 @@ def test_warp_rejects_cpu_and_grad(cuda_device):
         cf.warp(torch.zeros(1, 1, 8, 8, device=cuda_device), torch.zeros(1, 2, 5, 5, device=cuda_device), -1.0)
 
 
+def test_zero_flow_gate_matches_the_reference_branch(cuda_device):
+    """`if not flow_final.any(): keep rec_img0 / states` (e2v_model.py:184-191) evaluated on the
+    device.  All-zero flow (incl. -0.0) -> outputs are the inputs (NOT the zero-flow warp, which shifts every pixel,
+    SURVEY F6); one non-zero or NaN element anywhere -> the ordinary warp; the whole step is capturable in a CUDA
+    graph and re-evaluates the predicate on every replay."""
+    img, codes, flow = (dev_t(a, cuda_device) for a in synth.warp_inputs(2, 64, 96, seed=3, code_channels=16, flow_kind="smooth"))
+    zero = torch.zeros_like(flow)
+    zero[1, 0, 5, 7] = -0.0
+    assert cf.flow_any(zero).item() == 0 and cf.flow_any(flow).item() == 1
+    odd = torch.zeros(1037, device=cuda_device)      # tail handling (n % 4 != 0)
+    assert cf.flow_any(odd).item() == 0
+    odd[-1] = 1e-30
+    assert cf.flow_any(odd).item() == 1
+    odd[-1] = float("nan")
+    assert cf.flow_any(odd).item() == 1
+    for mode in ("forward", "backward"):
+        wi, wz = cf.warp_frame_and_codes(img, codes, zero, mode, skip_zero_flow=True)
+        assert torch.equal(wi, img) and torch.equal(wz, codes)
+        ref_i, ref_z = ref_port.warp_frame_and_codes(img.cpu(), codes.cpu(), zero.cpu(), mode)
+        assert (ref_i - img.cpu()).abs().max() > 1e-3          # the un-gated zero-flow warp is not the identity ...
+        ui, uz = cf.warp_frame_and_codes(img, codes, zero, mode)
+        assert (ui.cpu() - ref_i).abs().max() <= 1e-4 and (uz.cpu() - ref_z).abs().max() <= 1e-4   # ... and we match it
+        one = zero.clone()
+        one[0, 1, 3, 3] = 2.5
+        gi, gz = cf.warp_frame_and_codes(img, codes, one, mode, skip_zero_flow=True)
+        ri, rz = ref_port.warp_frame_and_codes(img.cpu(), codes.cpu(), one.cpu(), mode)
+        assert (gi.cpu() - ri).abs().max() <= 1e-4 and (gz.cpu() - rz).abs().max() <= 1e-4
+    # graph capture: the predicate is re-evaluated on the device at every replay
+    fbuf = flow.clone()
+    s = torch.cuda.Stream(cuda_device)
+    with torch.cuda.stream(s):
+        cf.warp_frame_and_codes(img, codes, fbuf, "forward", skip_zero_flow=True)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            gi, gz = cf.warp_frame_and_codes(img, codes, fbuf, "forward", skip_zero_flow=True)
+        g.replay()
+        torch.cuda.synchronize()
+        ri, _ = ref_port.warp_frame_and_codes(img.cpu(), codes.cpu(), flow.cpu(), "forward")
+        assert (gi.cpu() - ri).abs().max() <= 1e-4
+        fbuf.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(gi, img) and torch.equal(gz, codes)
+
+
 # -------------------------------------------------------------------- fwl ---
 def test_fwl_golden_and_config_shape(golden, cuda_device):
     """voxel_warping_flow_loss (FWL metric): warped channels within the warp tolerance
