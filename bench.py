@@ -477,7 +477,7 @@ def run_ours(args, cfg):
     }
     share = {k: v["ms_per_launch"] * (cfg["lookups"] if k == "corr_lookup" else 1) for k, v in kernels.items()}
     roof = dict(kernels["corr_lookup"])
-    roof.update({"kernel": "corr_lookup_r4l4_kernel<16>", "traffic": ncu_traffic("corr_lookup_r4l4_kernel"), "peak_source": peak_src,
+    roof.update({"kernel": "corr_lookup_r4l4_kernel", "traffic": ncu_traffic("corr_lookup_r4l4_kernel"), "peak_source": peak_src,
                  "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full "
                                  "capture (profiles/r01/step_kernels_ncu_full.txt); the 8 MB output of a single replayed "
                                  "launch stays in the 126 MB L2, so the write-back is not inside the kernel's window",

@@ -51,15 +51,15 @@ constexpr int kLookupThreads = 256;
 //            column share their horizontal interpolation, so a task is 20 LDS + 10 horizontal + 9
 //            vertical lerps and 9 coalesced stores (32 lanes = 32 consecutive queries of one channel
 //            = one 128-byte line of the channel-major output) instead of 36 LDS + 36 FMA.
-template <int QT>
+// QT (queries per CTA, even, <= 32) is a run-time argument: the host picks the value that balances the CTAs over the
+// SMs (see launch_lookup_r4l4).
 __global__ void __launch_bounds__(kLookupThreads)
-corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict__ coords, float *__restrict__ out, int N) {
+corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict__ coords, float *__restrict__ out, int N,
+                        int QT) {
     extern __shared__ float smem[];
     constexpr int PS = 401;                    // 4 levels x 10 x 10, odd stride between queries
     constexpr int NW = kLookupThreads / 32;
-    constexpr int QPW = QT / NW;               // queries gathered by one warp
-    constexpr int U = 2;                       // queries in flight per pass
-    static_assert(QPW % U == 0, "queries per warp must be even");
+    constexpr int U = 2;                       // queries in flight per pass (QT is even)
     float *patch = smem;                       // [QT][PS]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -68,7 +68,9 @@ corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__rest
     if (tid == 0) CF_TRACE_AT(0);
 
     // phase-B coordinates of this lane's query: requested now, first used after the barrier
-    const int qiB = lane % QT, qB = q0 + qiB;
+    const int TPW = 32 / QT;                   // tasks per warp pass in phase B
+    const int qiB = lane % QT, tslot = lane / QT;
+    const int qB = (tslot < TPW) ? q0 + qiB : N;   // lanes beyond TPW * QT idle in phase B
     float cxB = 0.f, cyB = 0.f;
     if (qB < N) {
         cxB = __ldg(cb + qB);
@@ -79,27 +81,27 @@ corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__rest
     {
         // clamp keeps (int) conversions defined for wild coordinates; anything this far out samples
         // only zero padding anyway (NaN clamps to the bound)
-        float cxs[QPW], cys[QPW];
-#pragma unroll
-        for (int u = 0; u < QPW; ++u) {
-            const int q = q0 + warp * QPW + u;
-            cxs[u] = q < N ? fminf(fmaxf(__ldg(cb + q), -1.0e6f), 1.0e6f) : 0.f;
-            cys[u] = q < N ? fminf(fmaxf(__ldg(cb + N + q), -1.0e6f), 1.0e6f) : 0.f;
-        }
         const int rg = lane / 10, col = lane - rg * 10;    // rg == 3: lanes 30, 31 idle
-        float *slot = patch + (warp * QPW) * PS + rg * 10 + col;
+#pragma unroll 1
+        for (int qq = U * warp; qq < QT; qq += U * NW) {   // this warp's query pairs
+            float cxs[U], cys[U];
 #pragma unroll
-        for (int qq = 0; qq < QPW; qq += U) {
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + qq + u;
+                cxs[u] = q < N ? fminf(fmaxf(__ldg(cb + q), -1.0e6f), 1.0e6f) : 0.f;
+                cys[u] = q < N ? fminf(fmaxf(__ldg(cb + N + q), -1.0e6f), 1.0e6f) : 0.f;
+            }
+            float *slot = patch + qq * PS + rg * 10 + col;
             float v[U][16];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int q = q0 + warp * QPW + qq + u;
+                const int q = q0 + qq + u;
                 const bool okq = q < N && rg < 3;
 #pragma unroll
                 for (int l = 0; l < 4; ++l) {
                     const float inv = 1.f / (float)(1 << l);  // exact: coords / 2**l
-                    const int X = (int)floorf(cxs[qq + u] * inv) - 4 + col;
-                    const int Y = (int)floorf(cys[qq + u] * inv) - 4 + rg;
+                    const int X = (int)floorf(cxs[u] * inv) - 4 + col;
+                    const int Y = (int)floorf(cys[u] * inv) - 4 + rg;
                     const int Hl = pyr.H[l], Wl = pyr.W[l];
                     const bool okx = okq && (unsigned)X < (unsigned)Wl;
                     const float *p = pyr.ptr[l] + ((size_t)b * N + q) * (Hl * Wl) + (Y * Wl + X);
@@ -118,7 +120,7 @@ corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__rest
                     for (int l = 0; l < 4; ++l)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < 3 || rg == 0) slot[(qq + u) * PS + l * 100 + 30 * k] = v[u][l * 4 + k];
+                            if (k < 3 || rg == 0) slot[u * PS + l * 100 + 30 * k] = v[u][l * 4 + k];
             }
         }
     }
@@ -128,12 +130,11 @@ corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__rest
 
     // ---- phase B ---------------------------------------------------------------------------
     if (qB < N) {
-        constexpr int TPW = 32 / QT;               // tasks per warp pass
         const float cx = fminf(fmaxf(cxB, -1.0e6f), 1.0e6f), cy = fminf(fmaxf(cyB, -1.0e6f), 1.0e6f);
         const float *pq = patch + qiB * PS;
         float *ob = out + (size_t)b * 324 * N + qB;
 #pragma unroll 1
-        for (int task = warp * TPW + lane / QT; task < 36; task += NW * TPW) {
+        for (int task = warp * TPW + tslot; task < 36; task += NW * TPW) {
             const int l = task / 9, i = task - l * 9;    // i -> x offset (transposed window)
             const float inv = 1.f / (float)(1 << l);
             const float sx = cx * inv, sy = cy * inv;
@@ -228,20 +229,34 @@ corr_lookup_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict_
 
 CF_DEFINE_TRACE_SETTER(cf_trace_buffer_lookup)
 
-template <int QT>
 static int launch_lookup_r4l4(const Pyramid &pyr, const float *coords, float *out, int B, int N, cudaStream_t stream) {
-    const size_t smem = (size_t)QT * 401 * sizeof(float);
+    // queries per CTA.  Up to about one wave of 16-query CTAs the launch is latency bound and 16 is the measured
+    // optimum (14 balances 6 144 queries better -- 3 CTAs on every SM -- but idles a gather warp and four lanes:
+    // 5.4 against 5.2 us).  Beyond that: the even value in [16, 32] with the smallest per-SM maximum
+    // ceil(CTAs / SMs) * QT (ties: larger).  Measured against fixed 32: 64x24x32 34.3 -> 31.9 us,
+    // 64x36x44 83.4 -> 62.7 us, 8x60x80 42.9 -> 36.3 us.
+    const int sms = sm_count();
+    int qt = 16;
+    if (ceil_div(N, 16) * B > 4 * (int64_t)sms) {
+        int64_t best = -1;
+        for (int cand = 32; cand >= 16; cand -= 2) {
+            const int64_t ctas = ceil_div(N, cand) * B;
+            const int64_t cost = ceil_div(ctas, sms) * cand;
+            if (best < 0 || cost < best) { best = cost; qt = cand; }
+        }
+    }
+    const size_t smem = (size_t)qt * 401 * sizeof(float);
     int dev = 0;
     CF_CUDA(cudaGetDevice(&dev));
     static bool opt_in[64] = {};
     if (!opt_in[dev & 63]) {
-        CF_CUDA(cudaFuncSetAttribute(corr_lookup_r4l4_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CF_CUDA(cudaFuncSetAttribute(corr_lookup_r4l4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 401 * (int)sizeof(float)));
         opt_in[dev & 63] = true;
     }
-    dim3 grid((unsigned)ceil_div(N, QT), B);
+    dim3 grid((unsigned)ceil_div(N, qt), B);
     // (programmatic dependent launch was tried here: with 12 lookups back to back in a graph it made
     //  each launch 1.4 us SLOWER on the B200 -- 8.8 vs 7.4 us -- so plain stream order is kept)
-    corr_lookup_r4l4_kernel<QT><<<grid, kLookupThreads, smem, stream>>>(pyr, coords, out, N);
+    corr_lookup_r4l4_kernel<<<grid, kLookupThreads, smem, stream>>>(pyr, coords, out, N, qt);
     CF_LAUNCH_CHECK("corr_lookup_r4l4_kernel");
     return CF_OK;
 }
@@ -291,8 +306,7 @@ extern "C" int cf_corr_lookup(const float *const *pyramid, const float *coords, 
     // 16 queries per CTA when the problem is small (more CTAs than SMs), else 32 (128-byte stores)
     const bool small = (int64_t)B * ceil_div(N, 32) < 4 * (int64_t)sm_count();
     if (radius == 4 && levels == 4) {
-        return small ? launch_lookup_r4l4<16>(pyr, coords, out, B, N, stream)
-                     : launch_lookup_r4l4<32>(pyr, coords, out, B, N, stream);
+        return launch_lookup_r4l4(pyr, coords, out, B, N, stream);
     }
     return small ? launch_lookup<16>(pyr, coords, out, B, N, levels, radius, stream)
                  : launch_lookup<32>(pyr, coords, out, B, N, levels, radius, stream);
