@@ -35,6 +35,11 @@
 // grid's sum / sum of squares / non-zero count, so the separate statistics pass disappears.  Correct (all parity
 // tests green) but 1.4-4x SLOWER end to end on the B200 (8x180x240: 24.4 against 16.6 us; 64x260x346: 543 against
 // 132 us): returning atomics cost far more than the pass over the L2-resident grid they save.
+// Also measured and dropped: statistics + normalisation as ONE pass (a CTA keeps its <= 32 KB slice of a window in
+// registers, publishes its partial, waits on a per-window arrival counter -- tickets make the wait deadlock-free --
+// and normalises out of registers: one read, one write, one launch).  Parity-green but slower than the two
+// kernels at every shape (8x180x240: 18.7 against 16.6 us; 8x480x640: 55.2 against 43.6 us): the ticket atomic
+// sits in front of every load address and the waiting CTAs hold their SM slots idle.
 // Time normalisation is fp64 with the reference's operation order
 // (mul, then div) in both modes, so bin assignment is identical.
 #include <cooperative_groups.h>
