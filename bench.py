@@ -258,7 +258,9 @@ def run_ours(args, cfg):
         return vox, outs, wi, wz
 
     # -- capture one CUDA graph per input set (launch-bound otherwise: ~20 kernels of a few us)
-    stream = torch.cuda.Stream(dev)
+    # the capturing stream carries the critical chain (build -> 12 dependent lookups): highest priority, so that its
+    # CTAs are placed first whenever the branch kernels (lowest priority) free resources
+    stream = torch.cuda.Stream(dev, priority=-1) if os.environ.get("CF_BENCH_PRIORITY", "1") == "1" else torch.cuda.Stream(dev)
     graphs, graphs_serial, keep = [], [], []
     with torch.cuda.stream(stream):
         for d in dev_sets:

@@ -27,6 +27,8 @@
 //            queries of the same channel = one 128-byte line of the
 //            channel-major output.  No output staging, no bank conflicts (odd
 //            stride => lanes hit distinct banks).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cf {
@@ -152,6 +154,13 @@ corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__rest
         }
     }
     if (tid == 0) CF_TRACE_AT(3);
+#ifdef CF_TRACE
+    if (tid == 0 && g_trace) {  // which SM ran this CTA (slot 4)
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kTraceSlots + 4] = smid + 1;
+    }
+#endif
 }
 
 // Generic radius / level count (runtime arguments): one element per thread and step.
@@ -244,6 +253,10 @@ static int launch_lookup_r4l4(const Pyramid &pyr, const float *coords, float *ou
             const int64_t cost = ceil_div(ctas, sms) * cand;
             if (best < 0 || cost < best) { best = cost; qt = cand; }
         }
+    }
+    if (const char *force = getenv("CF_LOOKUP_QT")) {  // experiments
+        const int f = atoi(force);
+        if (f >= 2 && f <= 32 && (f & 1) == 0) qt = f;
     }
     const size_t smem = (size_t)qt * 401 * sizeof(float);
     int dev = 0;

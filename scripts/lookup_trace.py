@@ -35,6 +35,7 @@ torch.cuda.synchronize()
 cf.corr_lookup(pyr, c0, 4, out=out)
 torch.cuda.synchronize()
 t = buf.cpu().numpy().reshape(ncta, slots)
+sm = t[t[:, 3] > 0][:, 4] - 1
 t = t[t[:, 3] > 0][:, :4]
 t0 = t[:, 0].min()
 print(f"{len(t)} CTAs; CTA start: median {np.median(t[:, 0] - t0) / 1e3:.2f} max {(t[:, 0].max() - t0) / 1e3:.2f} us; "
@@ -42,3 +43,17 @@ print(f"{len(t)} CTAs; CTA start: median {np.median(t[:, 0] - t0) / 1e3:.2f} max
 seg = (t - t[:, :1]) / 1e3
 print("per-CTA medians since CTA start (us): gathered %.2f, barrier passed %.2f, stored %.2f" % tuple(np.median(seg[:, 1:], axis=0)))
 print("per-CTA 95th pct                     : gathered %.2f, barrier passed %.2f, stored %.2f" % tuple(np.percentile(seg[:, 1:], 95, axis=0)))
+
+# per-SM view: does the tail follow the number of CTAs an SM received?
+import collections
+per_sm = collections.defaultdict(list)
+for k in range(len(t)):
+    per_sm[int(sm[k])].append((t[k, 3] - t0) / 1e3)
+by_count = collections.defaultdict(list)
+for s_, ends in per_sm.items():
+    by_count[len(ends)].append(max(ends))
+for n in sorted(by_count):
+    v = np.array(by_count[n])
+    print(f"SMs with {n} CTA(s): {len(v):3d}; last CTA end median {np.median(v):.2f} max {v.max():.2f} us")
+slow = sorted(per_sm.items(), key=lambda kv: -max(kv[1]))[:8]
+print("slowest SMs:", ", ".join(f"sm{s_}:{len(e)}cta:{max(e):.2f}" for s_, e in slow))
