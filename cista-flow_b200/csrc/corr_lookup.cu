@@ -49,8 +49,8 @@ constexpr int kLookupThreads = 256;
 //            shared-memory slot are loop constants and a row costs one compare + one predicated LDG;
 //            the 16 loads of a query (two queries per pass: 32 per lane) are issued before the
 //            first shared-memory store;
-//   phase B  thread <-> (query = lane, task = (level, window column i)): the 9 samples of a window
-//            column share their horizontal interpolation, so a task is 20 LDS + 10 horizontal + 9
+//   phase B  thread <-> (query = lane, level, group of window columns i): the 9 samples of a window
+//            column share their horizontal interpolation, so a column is 20 LDS + 10 horizontal + 9
 //            vertical lerps and 9 coalesced stores (32 lanes = 32 consecutive queries of one channel
 //            = one 128-byte line of the channel-major output) instead of 36 LDS + 36 FMA.
 // QT (queries per CTA, even, <= 32) is a run-time argument: the host picks the value that balances the CTAs over the
@@ -132,21 +132,22 @@ corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__rest
 
     // ---- phase B ---------------------------------------------------------------------------
     if (qB < N) {
-        const float cx = fminf(fmaxf(cxB, -1.0e6f), 1.0e6f), cy = fminf(fmaxf(cyB, -1.0e6f), 1.0e6f);
-        const float *pq = patch + qiB * PS;
-        float *ob = out + (size_t)b * 324 * N + qB;
+        // the NW * TPW (8 or 16) thread slots of a query split into 4 levels x G window-column groups: a thread's
+        // level -- hence its fractions, patch and output base -- is fixed, its columns are ig, ig + G, ...
+        const int slot = warp * TPW + tslot, G = (NW * TPW) >> 2;
+        const int l = slot & 3, ig = slot >> 2;
+        const float inv = __int_as_float(0x3f800000 - (l << 23));   // 2**-l, exact: coords / 2**l
+        const float sx = fminf(fmaxf(cxB, -1.0e6f), 1.0e6f) * inv, sy = fminf(fmaxf(cyB, -1.0e6f), 1.0e6f) * inv;
+        const float fx = sx - floorf(sx), fy = sy - floorf(sy);
+        const float gx = 1.f - fx, gy = 1.f - fy;
+        const float *pp = patch + qiB * PS + l * 100 + ig;
+        float *o = out + (size_t)b * 324 * N + qB + (size_t)(l * 81 + ig * 9) * N;
+        const size_t o_step = (size_t)(9 * G) * N;
 #pragma unroll 1
-        for (int task = warp * TPW + tslot; task < 36; task += NW * TPW) {
-            const int l = task / 9, i = task - l * 9;    // i -> x offset (transposed window)
-            const float inv = 1.f / (float)(1 << l);
-            const float sx = cx * inv, sy = cy * inv;
-            const float fx = sx - floorf(sx), fy = sy - floorf(sy);
-            const float gx = 1.f - fx, gy = 1.f - fy;
-            const float *pp = pq + l * 100 + i;
-            float *o = ob + (size_t)(l * 81 + i * 9) * N;
+        for (int i = ig; i < 9; i += G, pp += G, o += o_step) {   // i -> x offset (transposed window)
             float top = pp[0] * gx + pp[1] * fx;
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {               // j -> y offset
+            for (int j = 0; j < 9; ++j) {                       // j -> y offset
                 const float bot = pp[(j + 1) * 10] * gx + pp[(j + 1) * 10 + 1] * fx;
                 o[(size_t)j * N] = top * gy + bot * fy;
                 top = bot;
