@@ -21,8 +21,8 @@ namespace cf {
 
 // implemented in corr_build_tc.cu
 int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int h, int w, float scale,
-                            float *level0, float *level1, int precision, void *ws, size_t ws_bytes, int flags,
-                            int *fused_level1, cudaStream_t stream);
+                            float *level0, float *level1, float *level2, float *level3, int precision, void *ws,
+                            size_t ws_bytes, int flags, int *fused_levels, cudaStream_t stream);
 bool corr_tensor_core_supported(int D, int h, int w);
 size_t corr_tc_workspace_bytes(int B, int D, int h, int w);
 
@@ -174,11 +174,12 @@ extern "C" int cf_corr_build(const float *fmap1, const float *fmap2, int B, int 
         CF_REQUIRE(corr_tensor_core_supported(D, h, w), CF_ERR_UNSUPPORTED,
                    "cf_corr_build: the tensor-core path needs D %% 32 == 0 and h*w %% 4 == 0 (got D=%d, h=%d, w=%d); "
                    "use CF_CORR_FP32", D, h, w);
-        int fused = 0;
+        int fused = 0;  // pyramid levels beyond level 0 that the GEMM's epilogue produced
         if (int rc = corr_volume_tensor_core(fmap1, fmap2, B, D, h, w, scale, pyramid[0],
-                                             levels > 1 ? pyramid[1] : nullptr, precision, ws, ws_bytes,
+                                             levels > 1 ? pyramid[1] : nullptr, levels > 2 ? pyramid[2] : nullptr,
+                                             levels > 3 ? pyramid[3] : nullptr, precision, ws, ws_bytes,
                                              tc_flags(), &fused, stream)) return rc;
-        if (fused) first_pooled = 2;
+        first_pooled = 1 + fused;
     }
     for (int l = first_pooled; l < levels; ++l) {
         if (l + 1 < levels) {  // two levels per launch

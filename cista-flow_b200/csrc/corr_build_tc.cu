@@ -90,6 +90,12 @@ struct Params {
                    //    9-12 per-atom boxes per stage made that issue rate the bound of the main loop (timeline)
     float *l0;
     float *l1;
+    // deep fusion (tiles of 8k whole target rows, i.e. feature maps up to 32 wide -- the 180x240 / DAVIS240 case):
+    // levels 2 and 3 are pooled from the level-1 rows while they are still in registers
+    int deep;      // 0: none, 1: level 2, 2: levels 2 and 3
+    int h2, w2, h3, w3;
+    float *l2;
+    float *l3;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------
@@ -534,6 +540,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (p.R != 0) {
                 const int y0 = nb * p.R;
                 float *l1map = p.l1 + ((size_t)b * p.N + (row_ok ? i : 0)) * p.h1 * p.w1;
+                float prev1[16], prev2[8];   // deep fusion: the previous level-1 / level-2 row of this query
                 int item = EPI_SPLIT - 1;  // an odd chunk count leaves the last warp of a quarter one item short: it starts here
                 for (int pr = 0; pr < p.R; pr += 2) {
                     const int y = y0 + pr;
@@ -544,18 +551,18 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         tmem_ld32(taddr + pr * p.w + xc, ra);
                         tmem_ld32(taddr + (pr + 1) * p.w + xc, rc);
                         tmem_ld_wait();
+                        // ATen avg_pool2d: ((a + b) + c) + d, then / 4, on the stored (scaled) values
+                        float o[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            float s = __uint_as_float(ra[2 * q]) * p.scale + __uint_as_float(ra[2 * q + 1]) * p.scale;
+                            s += __uint_as_float(rc[2 * q]) * p.scale;
+                            s += __uint_as_float(rc[2 * q + 1]) * p.scale;
+                            o[q] = s * 0.25f;
+                        }
                         if (row_ok && !(p.ablate & 1)) {
-                            // ATen avg_pool2d: ((a + b) + c) + d, then / 4, on the stored (scaled) values
                             float *dst = l1map + (size_t)(y >> 1) * p.w1 + (xc >> 1);
                             const int npool = min(16, p.w1 - (xc >> 1));
-                            float o[16];
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) {
-                                float s = __uint_as_float(ra[2 * q]) * p.scale + __uint_as_float(ra[2 * q + 1]) * p.scale;
-                                s += __uint_as_float(rc[2 * q]) * p.scale;
-                                s += __uint_as_float(rc[2 * q + 1]) * p.scale;
-                                o[q] = s * 0.25f;
-                            }
                             if (vec4_l1) {
 #pragma unroll
                                 for (int q = 0; q < 4; ++q)
@@ -565,6 +572,46 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                                 for (int q = 0; q < 8; ++q)
                                     if (2 * q < npool) *(reinterpret_cast<float2 *>(dst) + q) = make_float2(o[2 * q], o[2 * q + 1]);
+                            }
+                        }
+                        if (p.deep) {   // w <= 32: this is the only 32-column strip of the row pair
+                            // ATen avg_pool2d again, on the level-1 (then level-2) values just stored
+                            const int r1g = y >> 1;
+                            if (r1g & 1) {
+                                float l2v[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    float s2 = prev1[2 * q] + prev1[2 * q + 1];
+                                    s2 += o[2 * q];
+                                    s2 += o[2 * q + 1];
+                                    l2v[q] = s2 * 0.25f;
+                                }
+                                const int r2g = r1g >> 1;
+                                if (row_ok && r2g < p.h2 && !(p.ablate & 1)) {
+                                    float *d2 = p.l2 + (((size_t)b * p.N + i) * p.h2 + r2g) * p.w2;   // w2 is even
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q)
+                                        if (2 * q < p.w2) *(reinterpret_cast<float2 *>(d2) + q) = make_float2(l2v[2 * q], l2v[2 * q + 1]);
+                                }
+                                if (p.deep > 1) {
+                                    if (r2g & 1) {
+                                        const int r3g = r2g >> 1;
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) {
+                                            float s3 = prev2[2 * q] + prev2[2 * q + 1];
+                                            s3 += l2v[2 * q];
+                                            s3 += l2v[2 * q + 1];
+                                            if (row_ok && r3g < p.h3 && q < p.w3 && !(p.ablate & 1))
+                                                p.l3[(((size_t)b * p.N + i) * p.h3 + r3g) * p.w3 + q] = s3 * 0.25f;
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int q = 0; q < 8; ++q) prev2[q] = l2v[q];
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) prev1[q] = o[q];
                             }
                         }
                     }
@@ -676,10 +723,10 @@ bool corr_tensor_core_supported(int D, int h, int w) {
 size_t corr_tc_workspace_bytes(int, int, int, int) { return 0; }
 
 // flags (debug/experiments, env CF_TC_FLAGS): bit1 = encode the tensor maps as plain FLOAT32 (operands are
-// then truncated, not rounded, to TF32), bit2 = never fuse the pooling, bit4 = per-atom 2-D TMA boxes even when N % 32 == 0.
+// then truncated, not rounded, to TF32), bit2 = never fuse the pooling, bit3 = fuse level 1 only, bit4 = per-atom 2-D TMA boxes even when N % 32 == 0.
 int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int h, int w, float scale, float *level0,
-                            float *level1, int precision, void *, size_t, int flags, int *fused_level1,
-                            cudaStream_t stream) {
+                            float *level1, float *level2, float *level3, int precision, void *, size_t, int flags,
+                            int *fused_levels, cudaStream_t stream) {
     using namespace tc;
     CF_REQUIRE(precision == CF_CORR_TF32, CF_ERR_UNSUPPORTED, "cf_corr_build: CF_CORR_3XTF32 is not implemented yet");
     CF_REQUIRE(aligned16(f1) && aligned16(f2) && aligned16(level0), CF_ERR_ALIGN, "cf_corr_build: tensors must be 16-byte aligned");
@@ -695,8 +742,23 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         R = 2 * (MAX_BN / (2 * w));
         if (R > h) R = h;
         while (R > 0 && (R - 1) * w + (int)align_up(w, 32) > MAX_BN) R -= 2;
+        // narrow maps: whole groups of 8 (or 4) rows per tile, so that levels 2 and 3 can be pooled in the epilogue too
+        if (!(flags & 8) && w <= 32 && w % 8 == 0) {
+            if (R >= 8 && h % 8 == 0) R &= ~7;
+            else if (R >= 4 && h % 4 == 0) R &= ~3;
+        }
     }
-    *fused_level1 = R > 0;
+    // levels this launch produces beyond level 0.  Levels 2 / 3 ride along when a tile holds whole groups of 4 / 8
+    // target rows (R % 4 == 0 / R % 8 == 0: maps up to 64 / 32 wide) and the widths halve evenly (flags bit3: off)
+    static_assert(EPI_SPLIT == 1, "the deep pooling keeps the previous level-1 row per epilogue thread");
+    p.deep = 0;
+    if (R > 0 && !(flags & 8) && w <= 32 && level2 != nullptr && aligned16(level2) && R % 4 == 0 && w % 8 == 0 && h % 4 == 0) {
+        p.deep = 1;
+        if (level3 != nullptr && R % 8 == 0 && w % 8 == 0 && h % 8 == 0) p.deep = 2;
+    }
+    p.h2 = h / 4; p.w2 = w / 4; p.h3 = h / 8; p.w3 = w / 8;
+    p.l2 = level2; p.l3 = level3;
+    *fused_levels = R > 0 ? 1 + p.deep : 0;
     p.stream_l0 = (int64_t)B * N * N * 4 > (64ll << 20);
     if (R > 0) {
         p.R = R;
