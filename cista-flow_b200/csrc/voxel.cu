@@ -809,7 +809,8 @@ extern "C" int cf_voxel_bin(const double *events, const int64_t *offsets, int64_
         // The host does not know the per-window event counts (offsets live on the device), so the
         // events of a chunk are budgeted with the batch average; kernels take device offsets.
         const size_t per_window = (size_t)cells * sizeof(float) + (size_t)(total / B + 1) * 32;
-        int chunk = (voxel_flags() & 1) ? B : (int)((96ull << 20) / per_window);
+        static const size_t budget_mb = [] { const char *e = getenv("CF_VOXEL_CHUNK_MB"); return e ? (size_t)atoi(e) : (size_t)96; }();
+        int chunk = (voxel_flags() & 1) ? B : (int)((budget_mb << 20) / per_window);
         if (chunk < 1) chunk = 1;
         if (chunk > B) chunk = B;
         if (preprocess != CF_PRE_NONE) {

@@ -21,6 +21,9 @@
 //     bounds it, not memory (timelines: scripts/warp_trace.py);
 //   * per-row cp.async.bulk (UBLKCP) for shapes without a 16-byte row pitch: ~70 cycles per issued
 //     copy, serialised per lane;
+//   * a second, smaller source box (40x20, 1.56x instead of 2.25x over-fetch) for tiles whose taps fit it: SLOWER
+//     (64x180x240: 185.5 against 179.3 us; 8x480x640: 156.6 against 152.9) -- L2 -> SM traffic is not the bound; the
+//     ncu source view puts the largest stall (17 %) on the wait for the stage to land;
 //   * 64x16 tiles + a 3x3 menu of tensor-map boxes (over-fetch 1.3x instead of 2.25x), 2 CTAs per SM:
 //     28 % / 42 % against 44 % / 57 % for this kernel at 180x240 / 480x640 -- occupancy (3 small CTAs,
 //     2 pixels per thread) beats bytes saved.
@@ -112,15 +115,19 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_
     const int H = jz.H, W = jz.W;
     const float *fb = flow + (size_t)b * 2 * fH * fW;
 
-    // ---- sample positions of this thread's two pixels (rows warp and warp + 8 of the tile)
+    // ---- sample positions of this thread's two pixels.  A warp covers two tile rows as two passes of 16 px x 2 rows
+    //      (lanes 0-15: row 2*warp, lanes 16-31: row 2*warp + 1; pass k: columns 16k .. 16k+15): consecutive box rows
+    //      are 48 floats = 16 banks apart, so the 16 + 16 lanes of a pass start on 32 distinct banks (-4 % at
+    //      64x180x240 against 32 lanes on one row; ncu still shows 1.67 wavefronts per LDS on a sheared flow)
     Taps taps[2];
     bool live[2];
     int x0a[2], y0a[2];
     int mnx = INT_MAX, mny = INT_MAX, mxx = -1, mxy = -1;
-    const int x = tx * TW + lane;
+    const int y = ty * TH + 2 * warp + (lane >> 4);
+    const int xl = tx * TW + (lane & 15);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        const int y = ty * TH + warp + 8 * k;
+        const int x = xl + 16 * k;
         live[k] = x < W && y < H;
         if (live[k]) {
             if (identity) {
@@ -168,7 +175,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_
 #pragma unroll
         for (int k = 0; k < 2; ++k)
             if (live[k]) {
-                const int p = (ty * TH + warp + 8 * k) * W + x;
+                const int p = y * W + xl + 16 * k;
                 for (int c0 = c_begin; c0 < c_end; c0 += 8) warp_pixel<8>(img_b, out_b, taps[k], p, c0, c_end, plane);
             }
         return;
@@ -207,7 +214,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             if (!live[j]) continue;
-            float *o = out_b + (size_t)c0 * plane + (size_t)(ty * TH + warp + 8 * j) * W + x;
+            float *o = out_b + (size_t)c0 * plane + (size_t)y * W + xl + 16 * j;
             const float *s0 = st + s00[j], *s1 = st + s01[j], *s2 = st + s10[j], *s3 = st + s11[j];
             const float w0 = taps[j].w00, w1 = taps[j].w01, w2 = taps[j].w10, w3 = taps[j].w11;
             float v[CC][4];  // all 32 tap loads before the first store (LDS/STG interleaving serialises on aliasing)
