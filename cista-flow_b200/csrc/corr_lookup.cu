@@ -134,8 +134,11 @@ corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__rest
     if (qB < N) {
         // the NW * TPW (8 or 16) thread slots of a query split into 4 levels x G window-column groups: a thread's
         // level -- hence its fractions, patch and output base -- is fixed, its columns are ig, ig + G, ...
+        // (the TPW lane groups of a warp take neighbouring column groups of the SAME level: their patch addresses then
+        //  differ by one float, and with the odd query stride the 32 lanes hit 31-32 distinct banks; with different
+        //  levels per lane group -- 100 floats = 4 banks apart -- nearly every LDS was a 2-way conflict)
         const int slot = warp * TPW + tslot, G = (NW * TPW) >> 2;
-        const int l = slot & 3, ig = slot >> 2;
+        const int l = slot / G, ig = slot - l * G;
         const float inv = __int_as_float(0x3f800000 - (l << 23));   // 2**-l, exact: coords / 2**l
         const float sx = fminf(fmaxf(cxB, -1.0e6f), 1.0e6f) * inv, sy = fminf(fmaxf(cyB, -1.0e6f), 1.0e6f) * inv;
         const float fx = sx - floorf(sx), fy = sy - floorf(sy);
