@@ -55,9 +55,14 @@ constexpr int kLookupThreads = 256;
 //            = one 128-byte line of the channel-major output) instead of 36 LDS + 36 FMA.
 // QT (queries per CTA, even, <= 32) is a run-time argument: the host picks the value that balances the CTAs over the
 // SMs (see launch_lookup_r4l4).
+// QT_CT = 16: compile-time value for the latency-bound small-problem case (5.2 against 5.5 us at configs[1]);
+// QT_CT = 0: run-time value (compile-time values for the larger counts were measured slower: the unrolled
+// multi-pair gather costs occupancy -- 64x24x32 34.7 against 31.5 us).
+template <int QT_CT>
 __global__ void __launch_bounds__(kLookupThreads)
 corr_lookup_r4l4_kernel(const __grid_constant__ Pyramid pyr, const float *__restrict__ coords, float *__restrict__ out, int N,
-                        int QT) {
+                        int qt_rt) {
+    const int QT = QT_CT > 0 ? QT_CT : qt_rt;
     extern __shared__ float smem[];
     constexpr int PS = 401;                    // 4 levels x 10 x 10, odd stride between queries
     constexpr int NW = kLookupThreads / 32;
@@ -267,13 +272,15 @@ static int launch_lookup_r4l4(const Pyramid &pyr, const float *coords, float *ou
     CF_CUDA(cudaGetDevice(&dev));
     static bool opt_in[64] = {};
     if (!opt_in[dev & 63]) {
-        CF_CUDA(cudaFuncSetAttribute(corr_lookup_r4l4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 401 * (int)sizeof(float)));
+        CF_CUDA(cudaFuncSetAttribute(corr_lookup_r4l4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 401 * (int)sizeof(float)));
+        CF_CUDA(cudaFuncSetAttribute(corr_lookup_r4l4_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 401 * (int)sizeof(float)));
         opt_in[dev & 63] = true;
     }
     dim3 grid((unsigned)ceil_div(N, qt), B);
     // (programmatic dependent launch was tried here: with 12 lookups back to back in a graph it made
     //  each launch 1.4 us SLOWER on the B200 -- 8.8 vs 7.4 us -- so plain stream order is kept)
-    corr_lookup_r4l4_kernel<<<grid, kLookupThreads, smem, stream>>>(pyr, coords, out, N, qt);
+    if (qt == 16) corr_lookup_r4l4_kernel<16><<<grid, kLookupThreads, smem, stream>>>(pyr, coords, out, N, qt);
+    else corr_lookup_r4l4_kernel<0><<<grid, kLookupThreads, smem, stream>>>(pyr, coords, out, N, qt);
     CF_LAUNCH_CHECK("corr_lookup_r4l4_kernel");
     return CF_OK;
 }
