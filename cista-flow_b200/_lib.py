@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("CISTAFLOW_LIB", os.path.join(_HERE, "libcistaflow.so"
 
 # enums of include/cistaflow.h
 VOXEL_ATOMIC, VOXEL_DETERMINISTIC, VOXEL_ATOMIC_L2, VOXEL_ATOMIC_TILED = 0, 1, 2, 3
-FLAVOUR_TORCH, FLAVOUR_NUMPY, FLAVOUR_POL = 0, 1, 2
+FLAVOUR_TORCH, FLAVOUR_NUMPY, FLAVOUR_POL, FLAVOUR_MVSEC = 0, 1, 2, 3
 PRE_NONE, PRE_STD, PRE_MAXMIN = 0, 1, 2
 CORR_TF32, CORR_FP32, CORR_3XTF32 = 0, 1, 2
 CORR_MAX_LEVELS = 6

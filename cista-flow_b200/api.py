@@ -7,6 +7,7 @@ from .event_process import (event_preprocess, event_preprocess_batched, event_pr
 from .flow_utils import FrameWarp, backWarp, flow_any, forwardWarp, warp, warp_frame_and_codes
 from .install import install, uninstall
 from .loss import voxel_warping_flow_loss
+from .mvsec_utils import eventsToVoxel, eventsToVoxelTorch, events_to_neg_pos_voxel_torch, events_to_voxel_torch
 
 __all__ = [
     "CistaFlowError", "LIB_PATH", "load_library",
@@ -16,4 +17,5 @@ __all__ = [
     "events_to_voxel_grid_pytorch", "pack_events", "pack_events_host",
     "FrameWarp", "backWarp", "flow_any", "forwardWarp", "warp", "warp_frame_and_codes",
     "install", "uninstall", "voxel_warping_flow_loss",
+    "eventsToVoxel", "eventsToVoxelTorch", "events_to_neg_pos_voxel_torch", "events_to_voxel_torch",
 ]

@@ -85,7 +85,7 @@ voxel_scatter_atomic_kernel(const double *__restrict__ ev, const int64_t *__rest
                 weights_f32(b, wl, wr);
             } else {
                 double dl, dr;
-                weights_f64(b, dl, dr);
+                weights_wide(b, flavour, dl, dr);
                 wl = (float)dl;
                 wr = (float)dr;
             }
@@ -160,7 +160,7 @@ voxel_cluster_kernel(const double *__restrict__ ev, const int64_t *__restrict__ 
                         weights_f32(bb, wl, wr);
                     } else {
                         double dl, dr;
-                        weights_f64(bb, dl, dr);
+                        weights_wide(bb, flavour, dl, dr);
                         wl = (float)dl;
                         wr = (float)dr;
                     }
@@ -414,6 +414,32 @@ det_accumulate_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restr
         float acc = 0.f;
         bool touched = false;
         int64_t e = pos;
+        if (flavour == CF_FLAVOUR_MVSEC) {
+            // one index_put_ per bin over the time-sorted events (MVSEC_utils.py:283-292): the events of bin-1 (their
+            // right weights) precede the events of this bin (their left weights); fp32 adds of fp32-cast weights
+            for (int64_t j = prev_s; j < prev_e; ++j) {
+                const Binned bb = bin_event(load_event(ev, vals[j]), w, nb, H, W, flavour);
+                double wl, wr;
+                weights_mvsec(bb, wl, wr);
+                acc = __fadd_rn(acc, (float)wr);
+                touched = true;
+            }
+            while (e < n && keys[e] == k) {
+                const Binned bb = bin_event(load_event(ev, vals[e]), w, nb, H, W, flavour);
+                if (bb.bin != bin) break;
+                double wl, wr;
+                weights_mvsec(bb, wl, wr);
+                acc = __fadd_rn(acc, (float)wl);
+                touched = true;
+                ++e;
+            }
+            if (touched) cell0[(int64_t)bin * planes * plane] = acc;
+            prev_s = pos;
+            prev_e = e;
+            pos = e;
+            if (prev_s == prev_e && (pos >= n || keys[pos] != k)) break;
+            continue;
+        }
         while (e < n && keys[e] == k) {  // left weights, ti == bin
             const Binned bb = bin_event(load_event(ev, vals[e]), w, nb, H, W, flavour);
             if (bb.bin != bin) break;
@@ -778,7 +804,9 @@ extern "C" int cf_voxel_bin(const double *events, const int64_t *offsets, int64_
     CF_REQUIRE(mode >= CF_VOXEL_ATOMIC && mode <= CF_VOXEL_ATOMIC_TILED, CF_ERR_INVALID_ARG, "cf_voxel_bin: bad mode %d", mode);
     const bool force_l2 = mode == CF_VOXEL_ATOMIC_L2, force_tiled = mode == CF_VOXEL_ATOMIC_TILED;
     if (force_l2 || force_tiled) mode = CF_VOXEL_ATOMIC;
-    CF_REQUIRE(flavour >= CF_FLAVOUR_TORCH && flavour <= CF_FLAVOUR_POL, CF_ERR_INVALID_ARG, "cf_voxel_bin: bad flavour %d", flavour);
+    CF_REQUIRE(flavour >= CF_FLAVOUR_TORCH && flavour <= CF_FLAVOUR_MVSEC, CF_ERR_INVALID_ARG, "cf_voxel_bin: bad flavour %d", flavour);
+    CF_REQUIRE(!(force_tiled && flavour == CF_FLAVOUR_MVSEC), CF_ERR_UNSUPPORTED,
+               "cf_voxel_bin: CF_VOXEL_ATOMIC_TILED does not implement CF_FLAVOUR_MVSEC");
     CF_REQUIRE(preprocess >= CF_PRE_NONE && preprocess <= CF_PRE_MAXMIN, CF_ERR_INVALID_ARG, "cf_voxel_bin: bad preprocess %d", preprocess);
     CF_REQUIRE(total == 0 || aligned16(events), CF_ERR_ALIGN, "cf_voxel_bin: events not 16-byte aligned");
     CF_REQUIRE(total < (1ll << 32), CF_ERR_INVALID_ARG, "cf_voxel_bin: more than 2^32 events in one call");
@@ -790,7 +818,7 @@ extern "C" int cf_voxel_bin(const double *events, const int64_t *offsets, int64_
         int rc = launch_cluster_path(events, offsets, B, nb, H, W, flavour, preprocess, hot_thr, out, cells, stream);
         if (rc != 1) return rc;  // 1 = grid too large for the cluster path -> global path below
     }
-    if (mode == CF_VOXEL_ATOMIC && !force_l2 && !(voxel_flags() & 4) &&
+    if (mode == CF_VOXEL_ATOMIC && !force_l2 && !(voxel_flags() & 4) && flavour != CF_FLAVOUR_MVSEC &&
         (force_tiled || use_tiled(total, B, (int64_t)nb * planes * H * W))) {
         const size_t base = align_up(cf_preprocess_workspace_bytes(B, 0), 256);
         const size_t need = voxel_tiled_workspace_bytes(total, B, nb, H, W, flavour);

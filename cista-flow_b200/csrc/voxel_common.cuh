@@ -54,7 +54,10 @@ struct Binned {
 __device__ __forceinline__ Binned bin_event(const Event &e, const Window &w, int nb, int H, int W, int flavour) {
     Binned r;
     // t* = (nb-1)*(t-t0)/dT : one rounding per operation, no contraction
-    const double tn = __ddiv_rn(__dmul_rn((double)(nb - 1), __dsub_rn(e.t, w.t0)), w.span);
+    // (MVSEC flavour: ((t-t0)/dT)*(nb-1), MVSEC_utils.py:281-282)
+    const double tn = flavour == CF_FLAVOUR_MVSEC
+                          ? __dmul_rn(__ddiv_rn(__dsub_rn(e.t, w.t0), w.span), (double)(nb - 1))
+                          : __ddiv_rn(__dmul_rn((double)(nb - 1), __dsub_rn(e.t, w.t0)), w.span);
     const double lo = floor(tn);
     r.ok = (lo >= 0.0) && (lo < (double)nb) && (e.x >= 0.0) && (e.y >= 0.0) && (e.x < (double)W) && (e.y < (double)H);
     r.bin = r.ok ? (int)lo : 0;
@@ -66,6 +69,8 @@ __device__ __forceinline__ Binned bin_event(const Event &e, const Window &w, int
         r.chan = (int)e.p;
         r.ok = r.ok && (e.p >= 0.0) && (e.p < 2.0);
         r.sgn = (e.p == 0.0) ? 1.0 : e.p;
+    } else if (flavour == CF_FLAVOUR_MVSEC) {
+        r.sgn = e.p;  // polarity / weight as given (MVSEC_utils.py:287): 0 contributes nothing
     } else {
         r.sgn = (e.p == 0.0) ? -1.0 : e.p;
     }
@@ -81,6 +86,19 @@ __device__ __forceinline__ void weights_f32(const Binned &b, float &wl, float &w
 __device__ __forceinline__ void weights_f64(const Binned &b, double &wl, double &wr) {
     wl = __dmul_rn(b.sgn, __dsub_rn(1.0, b.dt));  // event_process.py:58-59
     wr = __dmul_rn(b.sgn, b.dt);
+}
+
+// MVSEC flavour: p * max(0, 1 - |t* - bin|) for bin = ti and ti + 1 (MVSEC_utils.py:286-287).  |t* - ti| = dt and
+// (ti + 1) - t* = 1 - dt are both exact in fp64, so the two weights are p * fl(1 - dt) and p * fl(1 - fl(1 - dt)).
+__device__ __forceinline__ void weights_mvsec(const Binned &b, double &wl, double &wr) {
+    const double one_minus = __dsub_rn(1.0, b.dt);
+    wl = __dmul_rn(b.sgn, one_minus);
+    wr = __dmul_rn(b.sgn, __dsub_rn(1.0, one_minus));
+}
+// fp64 weights of the non-TORCH flavours
+__device__ __forceinline__ void weights_wide(const Binned &b, int flavour, double &wl, double &wr) {
+    if (flavour == CF_FLAVOUR_MVSEC) weights_mvsec(b, wl, wr);
+    else weights_f64(b, wl, wr);
 }
 
 struct alignas(16) Partial {

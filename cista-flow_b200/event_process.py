@@ -45,7 +45,8 @@ _MODES = {"atomic": _lib.VOXEL_ATOMIC, "deterministic": _lib.VOXEL_DETERMINISTIC
           # partition + shared-memory tiles (no global atomics)
           "atomic_l2": _lib.VOXEL_ATOMIC_L2, "atomic_tiled": _lib.VOXEL_ATOMIC_TILED}
 _PRE = {None: _lib.PRE_NONE, "none": _lib.PRE_NONE, "std": _lib.PRE_STD, "maxmin": _lib.PRE_MAXMIN}
-_FLAVOURS = {"torch": _lib.FLAVOUR_TORCH, "numpy": _lib.FLAVOUR_NUMPY, "pol": _lib.FLAVOUR_POL}
+_FLAVOURS = {"torch": _lib.FLAVOUR_TORCH, "numpy": _lib.FLAVOUR_NUMPY, "pol": _lib.FLAVOUR_POL,
+             "mvsec": _lib.FLAVOUR_MVSEC}
 
 
 def _device() -> torch.device:

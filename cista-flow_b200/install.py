@@ -10,6 +10,9 @@ therefore rebinds the names *in every reference module that imported them*:
   utils.flow_utils           backWarp, forwardWarp, FrameWarp
   e2v.e2v_model, loss        FrameWarp
   loss, test_wo_flow, test_mvsec   voxel_warping_flow_loss (part "fwl")
+  data_readers.MVSEC_utils, data_readers.MVSEC, utils.event_uitls (DCEIFlow)
+                             eventsToVoxel, eventsToVoxelTorch, events_to_voxel_torch, events_to_neg_pos_voxel_torch
+                             (part "mvsec": the second voxeliser)
   ERAFT.corr, ERAFT.eraft    CorrBlock
   DCEIFlow.core.corr.raft_corr, DCEIFlow.DCEIFlow   CorrBlock
 
@@ -24,6 +27,7 @@ import sys
 
 from . import corr, event_process, flow_utils
 from . import loss as loss_mod
+from . import mvsec_utils
 
 _VOXEL = {name: getattr(event_process, name) for name in (
     "events_to_voxel_grid", "events_to_voxel_grid_pol", "events_to_voxel_grid_pytorch",
@@ -31,19 +35,23 @@ _VOXEL = {name: getattr(event_process, name) for name in (
 _WARP = {name: getattr(flow_utils, name) for name in ("backWarp", "forwardWarp", "FrameWarp")}
 _CORR = {"CorrBlock": corr.CorrBlock}
 _FWL = {"voxel_warping_flow_loss": loss_mod.voxel_warping_flow_loss}
+_MVSEC = {name: getattr(mvsec_utils, name) for name in (
+    "eventsToVoxel", "eventsToVoxelTorch", "events_to_voxel_torch", "events_to_neg_pos_voxel_torch")}
 
 # module -> symbols to rebind there (only names the module already has are touched)
 TARGETS = {
     "utils.event_process": (_VOXEL,),
     "data_readers.video_readers": (_VOXEL,),
     "data_readers.train_data_loaders": (_VOXEL,),
-    "data_readers.MVSEC": (_VOXEL,),
     "test_noeval": (_VOXEL,),
     "utils.flow_utils": (_WARP,),
     "e2v.e2v_model": (_WARP,),
     "loss": (_WARP, _FWL),
     "test_wo_flow": (_FWL,),
     "test_mvsec": (_FWL,),
+    "data_readers.MVSEC_utils": (_MVSEC,),
+    "data_readers.MVSEC": (_VOXEL, _MVSEC),
+    "DCEIFlow.utils.event_uitls": (_MVSEC,),
     "ERAFT.corr": (_CORR,),
     "ERAFT.eraft": (_CORR,),
     "DCEIFlow.core.corr.raft_corr": (_CORR,),
@@ -53,9 +61,9 @@ TARGETS = {
 _saved: dict[tuple[str, str], object] = {}
 
 
-def install(import_missing: bool = True, parts=("voxel", "warp", "corr", "fwl")) -> list[str]:
+def install(import_missing: bool = True, parts=("voxel", "warp", "corr", "fwl", "mvsec")) -> list[str]:
     """Rebind; returns the list of ``module.symbol`` names that were replaced."""
-    groups = {"voxel": _VOXEL, "warp": _WARP, "corr": _CORR, "fwl": _FWL}
+    groups = {"voxel": _VOXEL, "warp": _WARP, "corr": _CORR, "fwl": _FWL, "mvsec": _MVSEC}
     active = [groups[p] for p in parts]
     done = []
     for modname, tables in TARGETS.items():

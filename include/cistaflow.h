@@ -70,6 +70,8 @@ CF_API const char *cf_last_kernel(void);
  *           utils/event_process.py:127-190  events_to_voxel_grid_pytorch (flavour TORCH)
  *           utils/event_process.py:75-123   events_to_voxel_grid_pol     (flavour POL)
  *           utils/event_process.py:193-239  event_preprocess(_pytorch)   (preprocess != NONE)
+ *           data_readers/MVSEC_utils.py:253-303  events_to_voxel_torch   (flavour MVSEC; SURVEY.md 8f rank 4;
+ *                                                same code in DCEIFlow/utils/event_uitls.py:91-141)
  * ------------------------------------------------------------------------- */
 typedef enum cf_voxel_mode {
     CF_VOXEL_ATOMIC = 0,        /* fast: fp32 atomics, sum order unspecified (<= 1e-5 rel.);  */
@@ -83,7 +85,11 @@ typedef enum cf_voxel_mode {
 typedef enum cf_voxel_flavour {
     CF_FLAVOUR_TORCH = 0, /* fp32 weights, fp32 adds                  (event_process.py:166-187) */
     CF_FLAVOUR_NUMPY = 1, /* fp64 weights, fp64 add rounded to fp32    (event_process.py:56-66)   */
-    CF_FLAVOUR_POL = 2    /* [nb,2,H,W], channel = polarity, |weights| (event_process.py:104-119) */
+    CF_FLAVOUR_POL = 2,   /* [nb,2,H,W], channel = polarity, |weights| (event_process.py:104-119) */
+    CF_FLAVOUR_MVSEC = 3  /* the second voxeliser: t* = ((t-t0)/dT)*(nb-1) (divide first), weight p*max(0,1-|t*-bin|)
+                             with p used AS IS (0 contributes nothing), fp64 weights cast to fp32, fp32 adds; per cell
+                             and bin the sequential order is "events of bin-1 (right weights) before events of bin"
+                             (MVSEC_utils.py:283-292: one index_put_ per bin over the time-sorted events) */
 } cf_voxel_flavour;
 
 typedef enum cf_preprocess {

@@ -124,6 +124,41 @@ def voxel_grid_torch(events: torch.Tensor, num_bins: int, width: int, height: in
     return grid.view(num_bins, height, width)
 
 
+def mvsec_voxel_torch(xs, ys, ts, ps, num_bins: int, height: int, width: int) -> torch.Tensor:
+    """``events_to_voxel_torch(..., temporal_bilinear=True)`` (data_readers/MVSEC_utils.py:253-303): one
+    ``index_put_(accumulate=True)`` per bin with weights ``ps * max(0, 1 - |t* - bin|)``, t* = (ts - ts[0]) / dT * (B-1).
+    The reference's ``torch.max(zeros_f32, f64)`` promotes to fp64, the product with the (integer or float) polarity
+    stays fp64 and is cast to fp32 for the accumulation (``events_to_image_torch``, :243-250)."""
+    xs, ys, ts, ps = (torch.as_tensor(a) for a in (xs, ys, ts, ps))
+    with torch.no_grad():
+        grid = torch.zeros((num_bins, height, width), dtype=torch.float32)
+        span = ts[-1] - ts[0]
+        tn = (ts - ts[0]) / span * (num_bins - 1)
+        rows, cols = ys.long(), xs.long()
+        for b in range(num_bins):
+            tri = torch.clamp(1.0 - torch.abs(tn - b), min=0.0)
+            grid[b].index_put_((rows, cols), (ps * tri).float(), accumulate=True)
+    return grid
+
+
+def mvsec_events_to_voxel(events_xytp: np.ndarray, num_bins: int, height: int, width: int,
+                          event_polarity: bool = False) -> np.ndarray:
+    """``eventsToVoxel`` (MVSEC_utils.py:384-403) on rows (x, y, t, p): ``eventsToXYTP(process=True)`` (:348-364)
+    narrows x, y, p to int32 and normalises t to [0, 1] in NumPy fp64 first; with ``event_polarity`` the positive
+    (p > 0) and non-positive events are binned with unit weights into separate grids, concatenated (:306-343)."""
+    xs = events_xytp[:, 0].astype(np.int32)
+    ys = events_xytp[:, 1].astype(np.int32)
+    ps = events_xytp[:, 3].astype(np.int32)
+    ts = events_xytp[:, 2]
+    ts = (ts - ts[0]) / (ts[-1] - ts[0])
+    if not event_polarity:
+        return mvsec_voxel_torch(xs, ys, ts, ps, num_bins, height, width).numpy()
+    pt = torch.from_numpy(ps)
+    pos = mvsec_voxel_torch(xs, ys, ts, torch.where(pt > 0, 1.0, 0.0), num_bins, height, width)
+    neg = mvsec_voxel_torch(xs, ys, ts, torch.where(pt <= 0, 1.0, 0.0), num_bins, height, width)
+    return torch.cat([pos, neg], 0).numpy()
+
+
 def preprocess_numpy(grid: np.ndarray, mode: str = "std", filter_hot_pixel: bool = False) -> np.ndarray:
     """``event_preprocess`` (utils/event_process.py:193-216); hot-pixel
     threshold 25/num_bins.  Returns float32 (see module docstring)."""

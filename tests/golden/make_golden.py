@@ -18,6 +18,8 @@ warp.npz    utils/flow_utils.py      forwardWarp / backWarp / FrameWarp, + the
                                      image+codes step of e2v/e2v_model.py:188-191
 corr.npz    ERAFT/corr.py, DCEIFlow/core/corr/raft_corr.py   pyramid + lookup
 fwl.npz     loss.py                  voxel_warping_flow_loss (FWL metric), both time directions
+mvsec.npz   data_readers/MVSEC_utils.py   eventsToVoxel / events_to_voxel_torch / events_to_neg_pos_voxel_torch
+                                     (the second voxeliser, temporal bilinear)
 trace_eiflow.npz / trace_eraft.npz
             hot-path calls recorded inside DCEIFlowCistaNet / ERAFTCistaNet
             (seeded random-init weights, base_channels=16 to keep the files
@@ -150,6 +152,33 @@ def make_fwl():
     zero = ref_loss.voxel_warping_flow_loss(torch.from_numpy(voxel), torch.zeros(2, 2, 36, 44))
     out["loss_zero_flow"] = np.float32(zero.item())
     save("fwl.npz", **out)
+
+
+# ------------------------------------------------------------------ mvsec ---
+def make_mvsec():
+    """The second voxeliser (data_readers/MVSEC_utils.py:253-303, 306-343, 384-403).  Its index_put_(accumulate=True)
+    is sequential on the CPU below 32768 elements (or with one thread): the fixtures stay below that size and pin
+    the thread count, so the outputs are deterministic."""
+    from data_readers import MVSEC_utils as mu
+    torch.set_num_threads(1)
+    out = {}
+    cases = {
+        "base": (3000, 30, 40, 21, "pm1"),        # polarities -1 / +1
+        "binary": (3000, 30, 40, 22, "01"),       # polarities 0 / 1 as stored by the MVSEC reader: 0 contributes nothing
+        "dense": (6000, 12, 16, 23, "pm1"),
+        "two": (2, 30, 40, 24, "pm1"),
+    }
+    for name, (n, h, w, seed, pol) in cases.items():
+        ev = synth.events(n, h, w, seed)                      # rows (t, x, y, p in {0,1})
+        p = ev[:, 3].copy() if pol == "01" else np.where(ev[:, 3] > 0, 1.0, -1.0)
+        xytp = np.stack([ev[:, 1], ev[:, 2], ev[:, 0], p], axis=1)       # MVSEC row order (x, y, t, p)
+        out[f"{name}/events_xytp"] = xytp
+        out[f"{name}/dims"] = np.array([5, h, w])
+        out[f"{name}/voxel"] = mu.eventsToVoxel(xytp.copy(), num_bins=5, height=h, width=w, event_polarity=False)
+        out[f"{name}/voxel_pol"] = mu.eventsToVoxel(xytp.copy(), num_bins=5, height=h, width=w, event_polarity=True)
+        xs, ys, ts, ps = mu.eventsToXYTP(xytp.copy(), process=True)
+        out[f"{name}/direct"] = mu.events_to_voxel_torch(xs, ys, ts, ps, 5, sensor_size=(h, w)).numpy()
+    save("mvsec.npz", **out)
 
 
 # ------------------------------------------------------------------- corr ---
@@ -285,6 +314,8 @@ if __name__ == "__main__":
         make_warp()
     if not only or "fwl" in only:
         make_fwl()
+    if not only or "mvsec" in only:
+        make_mvsec()
     if not only or "corr" in only:
         make_corr()
     if not only or "trace" in only:

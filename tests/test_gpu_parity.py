@@ -403,6 +403,43 @@ def test_warp_rejects_cpu_and_grad(cuda_device):
         cf.warp(torch.zeros(1, 1, 8, 8, device=cuda_device), torch.zeros(1, 2, 5, 5, device=cuda_device), -1.0)
 
 
+# ---------------------------------------------------------- second voxeliser ---
+@pytest.mark.parametrize("case", ["base", "binary", "dense", "two"])
+def test_mvsec_voxeliser_golden(golden, cuda_device, case):
+    """eventsToVoxel / events_to_voxel_torch (data_readers/MVSEC_utils.py) = CF_FLAVOUR_MVSEC:
+    deterministic mode bit-exact against the reference's own outputs (its per-bin index_put_ is sequential at these
+    sizes), atomic mode within the voxel tolerance; both the signed grid and the positive / negative split."""
+    g = golden("mvsec")
+    ev = g[f"{case}/events_xytp"]
+    nb, h, w = (int(v) for v in g[f"{case}/dims"])
+    for pol, key in ((False, "voxel"), (True, "voxel_pol")):
+        det = cf.eventsToVoxel(ev.copy(), num_bins=nb, height=h, width=w, event_polarity=pol, mode="deterministic")
+        assert isinstance(det, np.ndarray) and det.dtype == np.float32 and det.shape == g[f"{case}/{key}"].shape
+        assert np.array_equal(bits(det), bits(g[f"{case}/{key}"]))
+        fast = cf.eventsToVoxelTorch(ev.copy(), nb, h, w, pol, mode="atomic")
+        assert fast.device.type == "cpu"            # comes back where the input lived, like the reference
+        assert_voxel_close(fast.numpy(), g[f"{case}/{key}"])
+    xs, ys, ts, ps = (torch.from_numpy(np.ascontiguousarray(ev[:, k])) for k in (0, 1, 2, 3))
+    direct = cf.events_to_voxel_torch(xs.int(), ys.int(), (ts - ts[0]) / (ts[-1] - ts[0]), ps.int(), nb, sensor_size=(h, w),
+                                      device=cuda_device, mode="deterministic")
+    assert direct.device.type == "cuda" and np.array_equal(bits(direct.cpu().numpy()), bits(g[f"{case}/direct"]))
+    with pytest.raises(NotImplementedError):
+        cf.events_to_voxel_torch(xs, ys, ts, ps, nb, sensor_size=(h, w), temporal_bilinear=False)
+
+
+def test_mvsec_voxeliser_config_shape(cuda_device):
+    """100 000 events at 480x640 (config 5): against the oracle port; conservation -- every event with a time stamp
+    inside the window spreads exactly its polarity over two bins."""
+    ev = synth.events(100000, 480, 640, 77)
+    p = np.where(ev[:, 3] > 0, 1.0, -1.0)
+    xytp = np.stack([ev[:, 1], ev[:, 2], ev[:, 0], p], axis=1)
+    ref = ref_port.mvsec_events_to_voxel(xytp, 5, 480, 640, False)
+    for mode in ("atomic", "deterministic"):
+        got = cf.eventsToVoxel(xytp.copy(), 5, 480, 640, mode=mode)
+        assert_voxel_close(got, ref)
+    assert abs(float(got.astype(np.float64).sum()) - float(p.sum())) <= 1e-2
+
+
 def test_zero_flow_gate_matches_the_reference_branch(cuda_device):
     """`if not flow_final.any(): keep rec_img0 / states` (e2v_model.py:184-191) evaluated on the
     device.  All-zero flow (incl. -0.0) -> outputs are the inputs (NOT the zero-flow warp, which shifts every pixel,

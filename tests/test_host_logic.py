@@ -134,6 +134,15 @@ def test_reference_signatures_are_mirrored():
     assert list(p)[1:5] == ["fmap1", "fmap2", "num_levels", "radius"] and p["num_levels"].default == 4 and p["radius"].default == 4
     g = cf.coords_grid(2, 3, 4)
     assert g.shape == (2, 2, 3, 4) and g[0, 0, 1, 2] == 2 and g[0, 1, 1, 2] == 1  # ch0 = x, ch1 = y
+    # the second voxeliser (data_readers/MVSEC_utils.py:253, 306, 384, 388)
+    p = sig(cf.events_to_voxel_torch).parameters
+    assert list(p)[:8] == ["xs", "ys", "ts", "ps", "B", "device", "sensor_size", "temporal_bilinear"]
+    assert p["sensor_size"].default == (180, 240) and p["temporal_bilinear"].default is True
+    assert list(sig(cf.events_to_neg_pos_voxel_torch).parameters)[:8] == list(p)[:8]
+    for fn in (cf.eventsToVoxel, cf.eventsToVoxelTorch):
+        q = sig(fn).parameters
+        assert list(q)[:6] == ["events", "num_bins", "height", "width", "event_polarity", "temporal_bilinear"]
+        assert q["num_bins"].default == 5 and q["event_polarity"].default is False
 
 
 def test_synth_generators_are_seeded_and_well_formed():
@@ -230,9 +239,11 @@ oc = types.ModuleType("omegaconf")
 class OmegaConf:
     create = staticmethod(lambda d: types.SimpleNamespace(**d))
 oc.OmegaConf = OmegaConf; sys.modules["omegaconf"] = oc
-import e2v.e2v_model, ERAFT.eraft, DCEIFlow.DCEIFlow, data_readers.video_readers
+import e2v.e2v_model, ERAFT.eraft, DCEIFlow.DCEIFlow, data_readers.video_readers, data_readers.MVSEC_utils
 import cistaflow_b200 as cf
 done = cf.install()
+assert data_readers.MVSEC_utils.eventsToVoxel is cf.eventsToVoxel          # the second voxeliser
+assert data_readers.MVSEC_utils.events_to_voxel_torch is cf.events_to_voxel_torch
 assert e2v.e2v_model.FrameWarp is cf.FrameWarp
 assert ERAFT.eraft.CorrBlock is cf.CorrBlock and DCEIFlow.DCEIFlow.CorrBlock is cf.CorrBlock
 assert data_readers.video_readers.events_to_voxel_grid is cf.events_to_voxel_grid

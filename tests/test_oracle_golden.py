@@ -145,6 +145,32 @@ def test_model_trace_replay_through_oracle(golden, trace):
     assert np.array_equal(half.numpy(), g["warp1/flow"])
 
 
+MVSEC_CASES = ["base", "binary", "dense", "two"]
+
+
+@pytest.mark.parametrize("case", MVSEC_CASES)
+def test_mvsec_voxeliser_ref_port_bit_exact(golden, case):
+    """The second voxeliser (data_readers/MVSEC_utils.py eventsToVoxel): the port reproduces the reference's own
+    outputs bit for bit (sequential index_put_: one thread, < 32768 events)."""
+    import torch
+    g = golden("mvsec")
+    ev = g[f"{case}/events_xytp"]
+    nb, h, w = (int(v) for v in g[f"{case}/dims"])
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        got = ref_port.mvsec_events_to_voxel(ev, nb, h, w, False)
+        got_pol = ref_port.mvsec_events_to_voxel(ev, nb, h, w, True)
+    finally:
+        torch.set_num_threads(threads)
+    assert got.dtype == np.float32 and got.shape == (nb, h, w) and got_pol.shape == (2 * nb, h, w)
+    assert np.array_equal(got.view(np.uint32), g[f"{case}/voxel"].view(np.uint32))
+    assert np.array_equal(got_pol.view(np.uint32), g[f"{case}/voxel_pol"].view(np.uint32))
+    assert np.array_equal(g[f"{case}/direct"], g[f"{case}/voxel"])
+    if case == "binary":   # 0 / 1 polarities: negative events contribute nothing (MVSEC_utils.py:355,364)
+        assert (g[f"{case}/voxel"] >= 0).all()
+
+
 def test_fwl_ref_port_bit_exact(golden):
     """loss.voxel_warping_flow_loss (FWL metric): the port reproduces the reference's warped channels and
     variance bit for bit, both time directions, and its zero-flow denominator."""
