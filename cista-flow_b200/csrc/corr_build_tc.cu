@@ -79,7 +79,7 @@ struct Params {
     int tiles_mp;  // pair kernel: pairs of query tiles per batch item (= ceil(tiles_m / 2)); total_tiles counts pairs
     int stages;      // shared-memory ring depth
     int stage_bytes; // A_BYTES + n_boxes_b * BOX_BYTES
-    int ablate;    // experiments (CF_TC_FLAGS bits 8-10): 1 = no level-0/1 stores, 2 = no MMAs, 4 = no operand loads, 8 = K-major instruction descriptor
+    int ablate;    // experiments (CF_TC_FLAGS bits 8-10): 1 = no level-0/1 stores, 2 = no MMAs, 4 = no operand loads, 8 = K-major instruction descriptor, 16 = no epilogue at all
     int b_half;    // pair kernel: fmap2 boxes per stage and CTA (half of the tile's columns each)
     int h1, w1;    // level-1 map size
     float scale;
@@ -259,6 +259,17 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t 
     d |= (uint64_t)(512u >> 4) << 32;                // stride byte offset (K)   bits [32,46)
     d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
     d |= (uint64_t)1 << 61;                          // layout type 1 = SWIZZLE_128B_BASE32B
+    return d;
+}
+// experiments only (ablate bit 8): canonical K-major 128B-swizzle descriptor over the same bytes (garbage results) --
+// times the MMA with the operand fetch pattern of a K-major layout
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(16u >> 4) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
     return d;
 }
 // instruction descriptor: D=f32, A=B=tf32, both MN-major, M=m (128, or 256 across a CTA pair), N=n
@@ -457,7 +468,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk) {
                         if (p.ablate & 2) continue;
-                        const uint64_t da = make_desc_mn_sw128(sa + kk * 1024), db = make_desc_mn_sw128(sb + kk * 1024);
+                        const uint64_t da = (p.ablate & 8) ? make_desc_k_sw128(sa + kk * 32) : make_desc_mn_sw128(sa + kk * 1024);
+                        const uint64_t db = (p.ablate & 8) ? make_desc_k_sw128(sb + kk * 32) : make_desc_mn_sw128(sb + kk * 1024);
                         if (CL == 2) umma_tf32_2sm(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
                         else umma_tf32(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
                     }
@@ -496,6 +508,14 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_after();
             if (tile == first_tile && threadIdx.x == 0) stamp(20);
             if (threadIdx.x == 0) TC_TRACE(tile_no, 12);
+            if (p.ablate & 16) {  // experiment: the epilogue reads nothing (MMA issue rate without TMEM read traffic)
+                tc_fence_before();
+                if (CL == 2) mbar_arrive_cluster(mapa_rank0(&tempty[acc]));
+                else mbar_arrive(&tempty[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                continue;
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)acc * MAX_BN;
             const int j0 = nb * p.BN;
             const int bn_valid = min(p.BN, p.N - j0);  // accumulator column c <-> target index j0 + c
@@ -786,7 +806,7 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // pairs of query tiles as one 256-row UMMA across two CTAs: measured slower than one CTA per tile on the B200
     // (8 x 60x80: 359 against 322 us, see the kernel's header), so only on request (flags bit6)
     const bool pair = (flags & 64) && p.tiles_m >= 2;
-    p.ablate = (flags >> 8) & 15;
+    p.ablate = (flags >> 8) & 31;
     p.tiles_mp = (int)ceil_div(p.tiles_m, 2);
     p.b_half = (int)ceil_div(p.BN_mma / 2, 32);
     if (pair) {
