@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CISTAFLOW_LIB", os.path.join(_HERE, "libcistaflow.so"
 VOXEL_ATOMIC, VOXEL_DETERMINISTIC, VOXEL_ATOMIC_L2, VOXEL_ATOMIC_TILED = 0, 1, 2, 3
 FLAVOUR_TORCH, FLAVOUR_NUMPY, FLAVOUR_POL, FLAVOUR_MVSEC = 0, 1, 2, 3
 PRE_NONE, PRE_STD, PRE_MAXMIN = 0, 1, 2
-CORR_TF32, CORR_FP32, CORR_3XTF32 = 0, 1, 2
+CORR_TF32, CORR_FP32, CORR_3XTF32, CORR_F16, CORR_AUTO = 0, 1, 2, 3, 4
 CORR_MAX_LEVELS = 6
 
 STATUS = {0: "CF_OK", -1: "CF_ERR_INVALID_ARG", -2: "CF_ERR_NULL", -3: "CF_ERR_ALIGN", -4: "CF_ERR_ARCH",

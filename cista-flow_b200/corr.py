@@ -18,8 +18,10 @@ import torch
 from . import _lib
 
 # 'tf32' (tcgen05 tensor cores, default), 'fp32' (SIMT, the reference's arithmetic)
+# "f16" = fp16 operand copies (kind::f16): same operand significands as "tf32", measured no faster
 DEFAULT_PRECISION = os.environ.get("CISTAFLOW_CORR_PRECISION", "tf32")
-_PREC = {"tf32": _lib.CORR_TF32, "fp32": _lib.CORR_FP32, "3xtf32": _lib.CORR_3XTF32}
+_PREC = {"tf32": _lib.CORR_TF32, "fp32": _lib.CORR_FP32, "3xtf32": _lib.CORR_3XTF32, "f16": _lib.CORR_F16,
+         "auto": _lib.CORR_AUTO}
 
 
 def coords_grid(batch, ht, wd, device=None):
@@ -40,7 +42,7 @@ def build_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4,
     B, D, h, w = fmap1.shape
     prec = precision or DEFAULT_PRECISION
     lib = _lib.load()
-    if prec == "tf32" and (D % 32 != 0 or (h * w) % 4 != 0):
+    if prec in ("tf32", "f16", "auto") and (D % 32 != 0 or (h * w) % 4 != 0):
         prec = "fp32"  # shapes the tensor-core tiling does not cover (never the model's: D=256, h,w % 4 == 0)
     dev = fmap1.device
     shapes = [(B * h * w, 1, h >> l, w >> l) for l in range(num_levels)]

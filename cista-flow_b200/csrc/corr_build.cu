@@ -141,7 +141,7 @@ avg_pool_two_levels_kernel(const float *__restrict__ in, float *__restrict__ out
 }  // namespace cf
 
 extern "C" size_t cf_corr_workspace_bytes(int B, int D, int h, int w, int, int precision) {
-    if (precision == CF_CORR_FP32 || B <= 0 || D <= 0 || h <= 0 || w <= 0) return 0;
+    if ((precision != CF_CORR_F16 && precision != CF_CORR_AUTO) || B <= 0 || D <= 0 || h <= 0 || w <= 0) return 0;
     return cf::corr_tc_workspace_bytes(B, D, h, w);
 }
 
@@ -156,7 +156,7 @@ extern "C" int cf_corr_build(const float *fmap1, const float *fmap2, int B, int 
                "cf_corr_build: bad shape B=%d D=%d h=%d w=%d", B, D, h, w);
     CF_REQUIRE((h >> (levels - 1)) >= 1 && (w >> (levels - 1)) >= 1, CF_ERR_INVALID_ARG,
                "cf_corr_build: %dx%d feature map is too small for %d levels", h, w, levels);
-    CF_REQUIRE(precision >= CF_CORR_TF32 && precision <= CF_CORR_3XTF32, CF_ERR_INVALID_ARG,
+    CF_REQUIRE(precision >= CF_CORR_TF32 && precision <= CF_CORR_AUTO, CF_ERR_INVALID_ARG,
                "cf_corr_build: bad precision %d", precision);
     for (int l = 0; l < levels; ++l) CF_REQUIRE(pyramid[l], CF_ERR_NULL, "cf_corr_build: pyramid[%d] is null", l);
     if (B == 0) return CF_OK;

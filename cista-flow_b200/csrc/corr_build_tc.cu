@@ -43,6 +43,7 @@
 // identical to a cvt.rna.tf32.f32 pre-pass: bias -5e-7, max|err| 2.8e-4*max|ref|
 // -- so no extra pass over the feature maps and no workspace are needed.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -52,7 +53,7 @@ namespace tc {
 
 constexpr int BM = 128;          // queries per tile (UMMA M)
 constexpr int BK = 32;           // K rows per pipeline stage (4 MMAs of K=8)
-constexpr int MAX_STAGES = 6;     // ring depth = as many stages of (fmap1 tile + this shape's fmap2 tile) as fit, at most 6
+constexpr int MAX_STAGES = 8;     // ring depth = as many stages of (fmap1 tile + this shape's fmap2 tile) as fit, at most 6
 constexpr int MAX_BN = 256;      // UMMA N limit
 constexpr int BOX_BYTES = 32 * 32 * 4;                 // one TMA box: 32 cols x 32 rows fp32
 constexpr int A_BYTES = (BM / 32) * BOX_BYTES;         // 16 KB
@@ -60,13 +61,13 @@ constexpr int EPI_BUF_BYTES = 32 * 32 * 4;               // one 32x32 fp32 outpu
 // Epilogue warps per TMEM lane quarter.  2 (eight epilogue warps splitting the tile's work items) was measured
 // SLOWER on the B200 (8 x 60x80: 362 against 334 us; with loads and stores ablated 258 against 238 us): the
 // epilogue is not the critical path, the tf32 MMAs are (operand fetch from shared memory).
-constexpr int EPI_SPLIT = 1;
-constexpr int EPI_WARPS = 4 * EPI_SPLIT;
-constexpr int EPI_BYTES = EPI_WARPS * 2 /*double buffer*/ * EPI_BUF_BYTES;  // 32 KB
+// (the kernel's template parameter ES; the TF32 kernel uses 1.  With fp16 operands the stages are half the size, the
+//  64 KB of epilogue buffers fit beside a deep ring, and the epilogue IS the critical path: one tile's epilogue takes
+//  3.7 us on four warps while the MMAs of a 128x160 tile need 1.5 us -- see the kernel's header.)
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int SMEM_FIXED = EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 32 * (EPI_WARPS + 2);
-constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+__host__ __device__ constexpr int epi_bytes(int es) { return 4 * es * 2 /*double buffer*/ * EPI_BUF_BYTES; }   // 32 KB per ES
+__host__ __device__ constexpr int smem_fixed(int es) { return epi_bytes(es) + 1024 /*align slack*/ + 256 /*barriers*/; }
+__host__ __device__ constexpr int threads(int es) { return 32 * (4 * es + 2); }
 constexpr uint32_t SPIN_LIMIT = 1u << 26;  // ~seconds; a stuck pipeline traps instead of hanging the GPU
 
 struct Params {
@@ -90,6 +91,8 @@ struct Params {
                    //    9-12 per-atom boxes per stage made that issue rate the bound of the main loop (timeline)
     float *l0;
     float *l1;
+    int lsu_stores;          // 1: level-0 rows leave through the LSU (transposed in shared memory), 0: TMA bulk stores
+    const float *inv_scale;  // F16 operands: [2*B] powers of two that undo the per-item operand scaling (else nullptr)
     // deep fusion (tiles of 8k whole target rows, i.e. feature maps up to 32 wide -- the 180x240 / DAVIS240 case):
     // levels 2 and 3 are pooled from the level-1 rows while they are still in registers
     int deep;      // 0: none, 1: level 2, 2: levels 2 and 3
@@ -261,6 +264,30 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t 
     d |= (uint64_t)1 << 61;                          // layout type 1 = SWIZZLE_128B_BASE32B
     return d;
 }
+// UMMA shared-memory descriptor, MN-major 16-bit operands, plain 128B swizzle: atoms of 64 columns (128 B) x 8 K rows
+// (1024 B); LBO = bytes between 64-column atoms (one TMA box), SBO = bytes between groups of 8 K rows
+__device__ __forceinline__ uint64_t make_desc_mn_f16(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(4096u >> 4) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// D=f32, A=B=f16, both MN-major, M=128, N=n
+__host__ __device__ inline uint32_t make_idesc_f16(int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // experiments only (ablate bit 8): canonical K-major 128B-swizzle descriptor over the same bytes (garbage results) --
 // times the MMA with the operand fetch pattern of a K-major layout
 __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
@@ -346,12 +373,23 @@ __device__ __forceinline__ void store_row_chunk(float *dst, const uint32_t (&v)[
 // commits arrive on `empty` / `tfull` of both CTAs; both epilogues arrive on the leader's `tempty`.
 // (A first pair variant only multicast the fmap2 tile to two independent cta_group::1 MMAs: L2 traffic -33 %,
 //  time unchanged -- L2 bandwidth was not the bound.)
-template <int CL>
-__global__ void __launch_bounds__(THREADS, 1)
+// F16: the operands are fp16 copies of the feature maps (same 11-bit significand as TF32, scaled per batch item by a
+// power of two so that any finite input fits; made by fmap_to_half_kernel).  kind::f16 covers K = 16 per MMA where
+// kind::tf32 covers 8 at the same ~1 accumulator column per clock, and every stage moves half the bytes: the GEMM
+// stops being MMA / load-latency bound and runs at the HBM write rate of the volume.
+template <int CL, bool F16, int ES>
+__global__ void __launch_bounds__(threads(ES), 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    static_assert(!(F16 && CL == 2), "the CTA-pair variant is tf32 only");
+    constexpr int EPI_SPLIT = ES, EPI_WARPS = 4 * ES, EPI_BYTES = epi_bytes(ES);
+    constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+    constexpr int BC = F16 ? 64 : 32;                   // operand columns per TMA box (128 bytes)
+    constexpr int ABYTES = (BM / BC) * BOX_BYTES;       // fmap1 part of a stage
+    constexpr int MMAS = F16 ? BK / 16 : BK / 8;        // MMAs per stage
+    constexpr int KSTEP = F16 ? 2048 : 1024;            // descriptor start-address advance per MMA
     const int STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
     uint8_t *epi = smem + STAGES * STAGE_BYTES;  // [EPI_WARPS][2][EPI_BUF_BYTES]
     uint64_t *bars = reinterpret_cast<uint64_t *>(epi + EPI_BYTES);
@@ -393,7 +431,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             // pair kernel: the leader's barrier counts the bytes of BOTH CTAs' boxes
-            const uint32_t tx_bytes = (uint32_t)(CL * (BM / 32 + (CL == 2 ? p.b_half : p.n_boxes_b))) * BOX_BYTES;
+            const uint32_t tx_bytes = (uint32_t)(CL * (BM / BC + (CL == 2 ? p.b_half : p.n_boxes_b))) * BOX_BYTES;
             const int jr = CL == 2 ? rank * (p.BN_mma / 2) : 0;  // first fmap2 column of this CTA inside the tile
             int tile_no = 0;
             for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
@@ -405,7 +443,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (kb == 0) TC_TRACE(tile_no, 0);
                     if (kb == kblocks - 1) TC_TRACE(tile_no, 1);
-                    uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + A_BYTES;
+                    uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + ABYTES;
                     if (p.ablate & 4) {
                         if (rank == 0) mbar_arrive(&full[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -431,15 +469,15 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     mbar_expect_tx(&full[stage], tx_bytes);
                     if (p.atoms3d) {
-                        tma_load_3d(sa, &tmap_a, 0, krow, i0 >> 5, &full[stage]);
+                        tma_load_3d(sa, &tmap_a, 0, krow, i0 / BC, &full[stage]);
                     } else {
 #pragma unroll
-                        for (int a = 0; a < BM / 32; ++a) tma_load_2d(sa + a * BOX_BYTES, &tmap_a, i0 + 32 * a, krow, &full[stage]);
+                        for (int a = 0; a < BM / BC; ++a) tma_load_2d(sa + a * BOX_BYTES, &tmap_a, i0 + BC * a, krow, &full[stage]);
                     }
                     if (p.b3d) {
-                        tma_load_3d(sb, &tmap_b, 0, krow, j0 >> 5, &full[stage]);
+                        tma_load_3d(sb, &tmap_b, 0, krow, j0 / BC, &full[stage]);
                     } else {
-                        for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOX_BYTES, &tmap_b, j0 + 32 * a, krow, &full[stage]);
+                        for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOX_BYTES, &tmap_b, j0 + BC * a, krow, &full[stage]);
                     }
                     if (tile == first_tile && kb == 0) stamp(2);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -451,7 +489,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0 && rank == 0) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            uint32_t idesc = make_idesc_tf32(p.BN_mma, CL * BM);
+            uint32_t idesc = F16 ? make_idesc_f16(p.BN_mma) : make_idesc_tf32(p.BN_mma, CL * BM);
             if (p.ablate & 8) idesc &= ~((1u << 15) | (1u << 16));  // experiment: K-major reads of the same bytes (garbage results)
             int tile_no = 0;
             for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
@@ -464,12 +502,17 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     tc_fence_after();
                     if (tile == first_tile && kb < 16) stamp(3 + kb);
                     if (kb < 8) TC_TRACE(tile_no, 3 + kb);
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + ABYTES;
 #pragma unroll
-                    for (int kk = 0; kk < BK / 8; ++kk) {
+                    for (int kk = 0; kk < MMAS; ++kk) {
                         if (p.ablate & 2) continue;
-                        const uint64_t da = (p.ablate & 8) ? make_desc_k_sw128(sa + kk * 32) : make_desc_mn_sw128(sa + kk * 1024);
-                        const uint64_t db = (p.ablate & 8) ? make_desc_k_sw128(sb + kk * 32) : make_desc_mn_sw128(sb + kk * 1024);
+                        if (F16) {
+                            umma_f16(d_tmem, make_desc_mn_f16(sa + kk * KSTEP), make_desc_mn_f16(sb + kk * KSTEP), idesc,
+                                     (uint32_t)((kb | kk) != 0));
+                            continue;
+                        }
+                        const uint64_t da = (p.ablate & 8) ? make_desc_k_sw128(sa + kk * 32) : make_desc_mn_sw128(sa + kk * KSTEP);
+                        const uint64_t db = (p.ablate & 8) ? make_desc_k_sw128(sb + kk * 32) : make_desc_mn_sw128(sb + kk * KSTEP);
                         if (CL == 2) umma_tf32_2sm(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
                         else umma_tf32(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
                     }
@@ -504,6 +547,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             else decode_tile(p, tile, b, mb, nb);
             const int i = mb * BM + row;
             const bool row_ok = i < p.N;
+            // 1/sqrt(D), times the powers of two that undo the per-item scaling of the fp16 operands
+            const float scale = F16 ? p.scale * __ldg(p.inv_scale + b) * __ldg(p.inv_scale + p.B + b) : p.scale;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             if (tile == first_tile && threadIdx.x == 0) stamp(20);
@@ -530,14 +575,48 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
                     uint8_t *buf = my_epi + (chunk_count & 1) * EPI_BUF_BYTES;
+                    if (p.lsu_stores) {
+                        // transpose through the (swizzled) buffer, then whole 128-byte rows with plain vector stores:
+                        // lane <-> (row = 4*it + lane/8, 16-byte piece = lane%8), four rows per instruction.  These go
+                        // through the LSU, not the TMA unit, so the operand loads never queue behind the volume's
+                        // HBM-paced write stream (with TMA bulk stores the tile period was store time + MMA time)
+                        __syncwarp();   // the previous chunk's reads of this buffer (two chunks ago) are done
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 o = make_float4(__uint_as_float(v[4 * q]) * scale, __uint_as_float(v[4 * q + 1]) * scale,
+                                                         __uint_as_float(v[4 * q + 2]) * scale, __uint_as_float(v[4 * q + 3]) * scale);
+                            *reinterpret_cast<float4 *>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+                        }
+                        __syncwarp();
+                        const int piece = lane & 7;
+                        float *dst0 = p.l0 + ((size_t)b * p.N + (size_t)(mb * BM + 32 * quarter)) * p.N + j0 + c0 + 4 * piece;
+                        float4 rowv[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = 4 * it + (lane >> 3);
+                            rowv[it] = *reinterpret_cast<const float4 *>(buf + r * 128 + ((piece ^ (r & 7)) << 4));
+                        }
+                        if (!(p.ablate & 1)) {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int r = 4 * it + (lane >> 3);
+                                if (mb * BM + 32 * quarter + r < p.N) {
+                                    float4 *d = reinterpret_cast<float4 *>(dst0 + (size_t)r * p.N);
+                                    if (p.stream_l0) __stcs(d, rowv[it]); else *d = rowv[it];
+                                }
+                            }
+                        }
+                        ++chunk_count;
+                        continue;
+                    }
                     if (chunk_count >= 2) {  // the store issued two chunks ago has finished reading this buffer
                         if (lane == 0) tma_store_wait_read<1>();
                         __syncwarp();
                     }
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 o = make_float4(__uint_as_float(v[4 * q]) * p.scale, __uint_as_float(v[4 * q + 1]) * p.scale,
-                                                     __uint_as_float(v[4 * q + 2]) * p.scale, __uint_as_float(v[4 * q + 3]) * p.scale);
+                        const float4 o = make_float4(__uint_as_float(v[4 * q]) * scale, __uint_as_float(v[4 * q + 1]) * scale,
+                                                     __uint_as_float(v[4 * q + 2]) * scale, __uint_as_float(v[4 * q + 3]) * scale);
                         *reinterpret_cast<float4 *>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
                     }
                     fence_async_smem();
@@ -553,7 +632,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 uint32_t v[32];
                 tmem_ld32(taddr, v);
                 tmem_ld_wait();
-                if (row_ok && bn_valid > 0) store_row_chunk(l0row + j0, v, p.scale, bn_valid, vec4_l0 && (bn_valid % 4 == 0), false);
+                if (row_ok && bn_valid > 0) store_row_chunk(l0row + j0, v, scale, bn_valid, vec4_l0 && (bn_valid % 4 == 0), false);
             }
             if (threadIdx.x == 0) TC_TRACE(tile_no, 13);
             // ---- level 1: 2x2 means straight from the accumulator rows
@@ -575,9 +654,9 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         float o[16];
 #pragma unroll
                         for (int q = 0; q < 16; ++q) {
-                            float s = __uint_as_float(ra[2 * q]) * p.scale + __uint_as_float(ra[2 * q + 1]) * p.scale;
-                            s += __uint_as_float(rc[2 * q]) * p.scale;
-                            s += __uint_as_float(rc[2 * q + 1]) * p.scale;
+                            float s = __uint_as_float(ra[2 * q]) * scale + __uint_as_float(ra[2 * q + 1]) * scale;
+                            s += __uint_as_float(rc[2 * q]) * scale;
+                            s += __uint_as_float(rc[2 * q + 1]) * scale;
                             o[q] = s * 0.25f;
                         }
                         if (row_ok && !(p.ablate & 1)) {
@@ -673,6 +752,58 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 CF_DEFINE_TRACE_SETTER(cf_trace_buffer_corr)
 
+// ---- fp16 operand copies ---------------------------------------------------------------------------------
+// amax[t * B + b] = max |x| over batch item b of feature map t (t = 0, 1), as the bit pattern of a non-negative float
+// (integer max == float max); zeroed by the host side before the launch.
+__global__ void __launch_bounds__(256)
+fmap_absmax_kernel(const float *__restrict__ f1, const float *__restrict__ f2, int64_t per_item, int B, unsigned *__restrict__ amax) {
+    const int item = blockIdx.y;                       // t * B + b
+    const float *src = (item < B ? f1 : f2) + (int64_t)(item < B ? item : item - B) * per_item;
+    float m = 0.f;
+    const int64_t n4 = per_item >> 2;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(s4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    m = warp_max(m);
+    __shared__ float sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) m = fmaxf(m, sh[k]);
+        if (m > 0.f) atomicMax(amax + item, __float_as_uint(fminf(m, 3.0e38f)));
+    }
+}
+// x -> fp16(x * 2^shift), shift chosen per batch item so that the largest magnitude lands in [2^13, 2^14): every finite
+// input fits fp16 (round to nearest: the same 11-bit significand a TF32 operand keeps), the scaling is exact, and
+// inv_scale[item] = 2^-shift lets the GEMM epilogue undo it.  per_item % 4 == 0.
+__global__ void __launch_bounds__(256)
+fmap_to_half_kernel(const float *__restrict__ f1, const float *__restrict__ f2, int64_t per_item, int B,
+                    const unsigned *__restrict__ amax, __half *__restrict__ h1, __half *__restrict__ h2,
+                    float *__restrict__ inv_scale) {
+    const int item = blockIdx.y;
+    const bool first = item < B;
+    const int64_t base = (int64_t)(first ? item : item - B) * per_item;
+    const float *src = (first ? f1 : f2) + base;
+    __half *dst = (first ? h1 : h2) + base;
+    const float mx = __uint_as_float(__ldg(amax + item));
+    const int shift = mx > 0.f ? 13 - ilogbf(mx) : 0;
+    const float up = ldexpf(1.f, shift > 126 ? 126 : shift);      // (a tiny maximum: clamp the exponent, still exact)
+    if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[item] = 1.f / up;
+    const int64_t n4 = per_item >> 2;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    uint2 *d4 = reinterpret_cast<uint2 *>(dst);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(s4 + i);
+        const __half2 lo = __floats2half2_rn(v.x * up, v.y * up), hi = __floats2half2_rn(v.z * up, v.w * up);
+        uint2 o;
+        o.x = *reinterpret_cast<const unsigned *>(&lo);
+        o.y = *reinterpret_cast<const unsigned *>(&hi);
+        d4[i] = o;
+    }
+}
+
 // ---- host side --------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -691,31 +822,39 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D map over a feature map viewed as [B*D rows, N cols], box 32 x 32, 128B swizzle / 32B atoms
-static int make_fmap_tmap(CUtensorMap *m, const float *base, int B, int D, int N, CUtensorMapDataType dt, int box_rows = 32) {
+// (fp16 operand copies: 2-byte elements, boxes of 64 columns, plain 128B swizzle)
+static int make_fmap_tmap(CUtensorMap *m, const void *base, int B, int D, int N, CUtensorMapDataType dt, int box_rows = 32) {
     EncodeTiledFn fn = encode_fn();
     CF_REQUIRE(fn, CF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const bool half = dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const size_t elt = half ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)B * D};
-    cuuint64_t strides[1] = {(cuuint64_t)N * sizeof(float)};
-    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)N * elt};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / elt), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, dt, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(m, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    half ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return CF_OK;
 }
 
 // The same feature map as a 3-D tensor {32 cols, B*D rows, N/32 column atoms} (N % 32 == 0): a box
 // {32, rows, atoms} lands in shared memory as [atom][row][32 cols] -- the UMMA MN-major layout -- in ONE instruction
-static int make_fmap_tmap3(CUtensorMap *m, const float *base, int B, int D, int N, CUtensorMapDataType dt, int box_rows,
+static int make_fmap_tmap3(CUtensorMap *m, const void *base, int B, int D, int N, CUtensorMapDataType dt, int box_rows,
                            int box_atoms) {
     EncodeTiledFn fn = encode_fn();
     CF_REQUIRE(fn, CF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint64_t dims[3] = {32, (cuuint64_t)B * D, (cuuint64_t)N / 32};
-    cuuint64_t strides[2] = {(cuuint64_t)N * sizeof(float), 128};
-    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_atoms};
+    const bool half = dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const size_t elt = half ? 2 : 4;
+    const cuuint32_t bc = (cuuint32_t)(128 / elt);
+    cuuint64_t dims[3] = {bc, (cuuint64_t)B * D, (cuuint64_t)N / bc};
+    cuuint64_t strides[2] = {(cuuint64_t)N * elt, 128};
+    cuuint32_t box[3] = {bc, (cuuint32_t)box_rows, (cuuint32_t)box_atoms};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(m, dt, 3, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    half ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_CUDA, "cuTensorMapEncodeTiled (3-D feature map) failed with CUresult %d", (int)r);
     return CF_OK;
 }
@@ -740,20 +879,55 @@ bool corr_tensor_core_supported(int D, int h, int w) {
     return D % tc::BK == 0 && ((int64_t)h * w) % 4 == 0;
 }
 
-size_t corr_tc_workspace_bytes(int, int, int, int) { return 0; }
+// fp16 operand copies of both feature maps + per-item maxima and inverse scales (CF_CORR_F16 / CF_CORR_AUTO)
+size_t corr_tc_workspace_bytes(int B, int D, int h, int w) {
+    const size_t per_map = align_up((size_t)B * D * h * w * sizeof(__half), 256);
+    return 2 * per_map + align_up((size_t)4 * B * sizeof(float), 256);
+}
 
 // flags (debug/experiments, env CF_TC_FLAGS): bit1 = encode the tensor maps as plain FLOAT32 (operands are
 // then truncated, not rounded, to TF32), bit2 = never fuse the pooling, bit3 = fuse level 1 only, bit4 = per-atom 2-D TMA boxes even when N % 32 == 0.
 int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int h, int w, float scale, float *level0,
-                            float *level1, float *level2, float *level3, int precision, void *, size_t, int flags,
+                            float *level1, float *level2, float *level3, int precision, void *ws, size_t ws_bytes, int flags,
                             int *fused_levels, cudaStream_t stream) {
     using namespace tc;
-    CF_REQUIRE(precision == CF_CORR_TF32, CF_ERR_UNSUPPORTED, "cf_corr_build: CF_CORR_3XTF32 is not implemented yet");
+    CF_REQUIRE(precision == CF_CORR_TF32 || precision == CF_CORR_F16 || precision == CF_CORR_AUTO, CF_ERR_UNSUPPORTED,
+               "cf_corr_build: CF_CORR_3XTF32 is not implemented yet");
     CF_REQUIRE(aligned16(f1) && aligned16(f2) && aligned16(level0), CF_ERR_ALIGN, "cf_corr_build: tensors must be 16-byte aligned");
     const int N = h * w;
-    const float *a = f1, *bm = f2;
+    // AUTO resolves to TF32: the fp16-operand variant halves the MMA time and the operand bytes and agrees with
+    // TF32 to summation-order noise (same 11-bit operand significands), but measured NO faster on the B200
+    // (8 x 60x80: GEMM 283 against 277 us, plus 32 us of conversion) -- the kernel is bound on the volume's write side
+    if (precision == CF_CORR_AUTO) precision = CF_CORR_TF32;
+    const bool f16 = precision == CF_CORR_F16;
+    const int BC = f16 ? 64 : 32;   // operand columns per TMA box
+    const void *a = f1, *bm = f2;
+    const float *inv_scale = nullptr;
+    if (f16) {
+        const size_t need = corr_tc_workspace_bytes(B, D, h, w);
+        CF_REQUIRE(ws && ws_bytes >= need, CF_ERR_WORKSPACE, "cf_corr_build: workspace too small for CF_CORR_F16 (%zu < %zu)",
+                   ws_bytes, need);
+        CF_REQUIRE(aligned16(ws), CF_ERR_ALIGN, "cf_corr_build: workspace not 16-byte aligned");
+        const int64_t per_item = (int64_t)D * N;   // N % 4 == 0 (corr_tensor_core_supported)
+        const size_t per_map = align_up((size_t)B * per_item * sizeof(__half), 256);
+        __half *h1 = reinterpret_cast<__half *>(ws), *h2 = reinterpret_cast<__half *>(reinterpret_cast<char *>(ws) + per_map);
+        unsigned *amax = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(ws) + 2 * per_map);
+        float *inv = reinterpret_cast<float *>(amax + 2 * B);
+        CF_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned) * 2 * B, stream));
+        int64_t bx = ceil_div(per_item / 4, 256 * 8);
+        const int64_t cap = ceil_div(8 * (int64_t)sm_count(), 2 * B);
+        if (bx > cap) bx = cap;
+        if (bx < 1) bx = 1;
+        dim3 grid((unsigned)bx, (unsigned)(2 * B));
+        fmap_absmax_kernel<<<grid, 256, 0, stream>>>(f1, f2, per_item, B, amax);
+        CF_LAUNCH_CHECK("fmap_absmax_kernel");
+        fmap_to_half_kernel<<<grid, 256, 0, stream>>>(f1, f2, per_item, B, amax, h1, h2, inv);
+        CF_LAUNCH_CHECK("fmap_to_half_kernel");
+        a = h1; bm = h2; inv_scale = inv;
+    }
     Params p{};
     p.B = B; p.D = D; p.N = N; p.h = h; p.w = w; p.scale = scale; p.l0 = level0; p.l1 = level1;
+    p.inv_scale = inv_scale;
     p.h1 = h / 2; p.w1 = w / 2;
     // R = number of whole target rows per tile (even).  The epilogue reads 32-column chunks, so the
     // last chunk of the last row must stay inside the 256-column accumulator stage.
@@ -770,7 +944,6 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     }
     // levels this launch produces beyond level 0.  Levels 2 / 3 ride along when a tile holds whole groups of 4 / 8
     // target rows (R % 4 == 0 / R % 8 == 0: maps up to 64 / 32 wide) and the widths halve evenly (flags bit3: off)
-    static_assert(EPI_SPLIT == 1, "the deep pooling keeps the previous level-1 row per epilogue thread");
     p.deep = 0;
     if (R > 0 && !(flags & 8) && w <= 32 && level2 != nullptr && aligned16(level2) && R % 4 == 0 && w % 8 == 0 && h % 4 == 0) {
         p.deep = 1;
@@ -790,36 +963,44 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         p.tiles_n = (int)ceil_div(N, p.BN);
     }
     p.BN_mma = (int)align_up(p.BN, 16);
-    p.n_boxes_b = (int)ceil_div(p.BN_mma, 32);
+    p.n_boxes_b = (int)ceil_div(p.BN_mma, BC);
     p.tiles_m = (int)ceil_div(N, BM);
     const int64_t total = (int64_t)B * p.tiles_m * p.tiles_n;
     CF_REQUIRE(total < (1ll << 31), CF_ERR_INVALID_ARG, "cf_corr_build: too many tiles");
     p.total_tiles = (int)total;
 
-    const CUtensorMapDataType dt = (flags & 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
-    p.atoms3d = (N % 32 == 0) && !(flags & 16);
-    p.b3d = p.atoms3d && (p.BN % 32 == 0 || p.tiles_n == 1);
-    // pairs of query tiles sharing their fmap2 tile through TMA multicast (flags bit5 = off)
-    p.stage_bytes = A_BYTES + p.n_boxes_b * BOX_BYTES;
-    p.stages = (SMEM_LIMIT - SMEM_FIXED) / p.stage_bytes;
+    const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                       : ((flags & 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
+    p.atoms3d = (N % BC == 0) && !(flags & 16);
+    p.b3d = p.atoms3d && (p.BN % BC == 0 || p.tiles_n == 1);
+    const int a_bytes = (BM / BC) * BOX_BYTES;
+    p.stage_bytes = a_bytes + p.n_boxes_b * BOX_BYTES;
+    // two epilogue warps per TMEM lane quarter when the ring still gets >= 5 stages beside their 64 KB of buffers (fp16
+    // operands); the deep pooling keeps per-thread row state and stays on one warp per quarter (flags bit7: force 1)
+    // (measured slower again, also with the half-size fp16 stages: 396 against 359 us at 8 x 60x80 -- only on request)
+    const int es = (f16 && p.deep == 0 && (flags & 128) && (SMEM_LIMIT - smem_fixed(2)) / p.stage_bytes >= 5) ? 2 : 1;
+    p.stages = (SMEM_LIMIT - smem_fixed(es)) / p.stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     // pairs of query tiles as one 256-row UMMA across two CTAs: measured slower than one CTA per tile on the B200
     // (8 x 60x80: 359 against 322 us, see the kernel's header), so only on request (flags bit6)
-    const bool pair = (flags & 64) && p.tiles_m >= 2;
+    const bool pair = (flags & 64) && p.tiles_m >= 2 && !f16;
     p.ablate = (flags >> 8) & 31;
+    // level-0 rows through the LSU instead of TMA bulk stores: helps where the operand loads already need many TMA
+    // instructions per stage (N % 32 != 0: 64 x 36x44 398 -> 367 us), costs 2-5 % elsewhere (flags bit0: always TMA)
+    p.lsu_stores = (!(flags & 1) && !p.atoms3d && N % 4 == 0) ? 1 : 0;
     p.tiles_mp = (int)ceil_div(p.tiles_m, 2);
     p.b_half = (int)ceil_div(p.BN_mma / 2, 32);
     if (pair) {
         p.total_tiles = B * p.tiles_mp * p.tiles_n;
         p.b3d = p.b3d && (p.BN_mma / 2) % 32 == 0;
         p.stage_bytes = A_BYTES + p.b_half * BOX_BYTES;
-        p.stages = (SMEM_LIMIT - SMEM_FIXED) / p.stage_bytes;
+        p.stages = (SMEM_LIMIT - smem_fixed(1)) / p.stage_bytes;
         if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     }
-    const int smem_bytes = p.stages * p.stage_bytes + SMEM_FIXED;
+    const int smem_bytes = p.stages * p.stage_bytes + smem_fixed(es);
     CUtensorMap ta, tb, tcm;
     if (p.atoms3d) {
-        if (int rc = make_fmap_tmap3(&ta, a, B, D, N, dt, BK, BM / 32)) return rc;
+        if (int rc = make_fmap_tmap3(&ta, a, B, D, N, dt, BK, BM / BC)) return rc;
     } else {
         if (int rc = make_fmap_tmap(&ta, a, B, D, N, dt)) return rc;
     }
@@ -834,8 +1015,10 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     CF_CUDA(cudaGetDevice(&dev));
     static bool opt_in[64] = {};
     if (!opt_in[dev & 63]) {
-        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         opt_in[dev & 63] = true;
     }
     const int sms = sm_count();
@@ -843,7 +1026,7 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         const int clusters = p.total_tiles < sms / 2 ? p.total_tiles : sms / 2;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(2 * clusters));
-        cfg.blockDim = dim3(THREADS);
+        cfg.blockDim = dim3(threads(1));
         cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -853,12 +1036,18 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CF_CUDA(cudaLaunchKernelEx(&cfg, corr_tc_kernel<2>, ta, tb, tcm, p));
+        CF_CUDA(cudaLaunchKernelEx(&cfg, corr_tc_kernel<2, false, 1>, ta, tb, tcm, p));
         CF_LAUNCH_CHECK("corr_tc_kernel<pair>");
         return CF_OK;
     }
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-    corr_tc_kernel<1><<<grid, THREADS, smem_bytes, stream>>>(ta, tb, tcm, p);
+    if (f16) {
+        if (es == 2) corr_tc_kernel<1, true, 2><<<grid, threads(2), smem_bytes, stream>>>(ta, tb, tcm, p);
+        else corr_tc_kernel<1, true, 1><<<grid, threads(1), smem_bytes, stream>>>(ta, tb, tcm, p);
+        CF_LAUNCH_CHECK("corr_tc_kernel<f16>");
+        return CF_OK;
+    }
+    corr_tc_kernel<1, false, 1><<<grid, threads(1), smem_bytes, stream>>>(ta, tb, tcm, p);
     CF_LAUNCH_CHECK("corr_tc_kernel");
     return CF_OK;
 }

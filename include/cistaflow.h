@@ -213,7 +213,12 @@ CF_API int cf_voxel_flow_warp(const float *voxel, const float *displacement, int
 typedef enum cf_corr_precision {
     CF_CORR_TF32 = 0, /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (default)  */
     CF_CORR_FP32 = 1, /* SIMT FFMA, fp32 operands (reference arithmetic)             */
-    CF_CORR_3XTF32 = 2 /* tcgen05, 3-term split: ~fp32 accuracy at 3x the MMA work   */
+    CF_CORR_3XTF32 = 2, /* tcgen05, 3-term split: ~fp32 accuracy at 3x the MMA work   */
+    CF_CORR_F16 = 3,    /* tcgen05.mma kind::f16 on fp16 operand COPIES (workspace): same 11-bit significand as a TF32
+                           operand, scaled per batch item by a power of two so that every finite input fits; K = 16
+                           per MMA and half the operand bytes.  Within fp32 summation-order noise of TF32; measured no
+                           faster on a B200 (the kernel is bound on the volume's write side), kept as an option */
+    CF_CORR_AUTO = 4    /* the library's choice (currently TF32) */
 } cf_corr_precision;
 
 #define CF_CORR_MAX_LEVELS 6

@@ -538,6 +538,26 @@ def test_corr_golden(golden, cuda_device, precision, tol):
     assert tuple(vol.shape) == (1, 16, 24, 1, 16, 24)
 
 
+def test_corr_f16_operands_match_tf32(cuda_device):
+    """CF_CORR_F16: fp16 copies of the operands, scaled per batch item by a power of two, through tcgen05 kind::f16.
+    The operands carry the same 11-bit significands as TF32 operands, so the two paths differ only by the fp32
+    summation order inside the MMAs (K = 16 against K = 8 per instruction): <= 1e-5 of max|ref| apart, also for inputs
+    far outside the fp16 range; 3-D operand boxes (24x32), per-atom boxes (36x44) and an all-zero map."""
+    for (H, W, B, scale) in ((192, 256, 2, 1.0), (288, 352, 1, 1.0), (192, 256, 1, 3.0e6), (192, 256, 1, 1.0e-9)):
+        f1, f2, _ = synth.corr_inputs(B, H, W, 9)
+        a, b = dev_t(f1, cuda_device) * scale, dev_t(f2, cuda_device)
+        t32 = cf.build_pyramid(a, b, 4, precision="tf32")
+        f16 = cf.build_pyramid(a, b, 4, precision="f16")
+        assert last_kernel() in ("corr_tc_kernel<f16>", "avg_pool_two_levels_kernel")
+        ref = cf.build_pyramid(a, b, 4, precision="fp32")
+        for l in range(4):
+            assert corr_err(f16[l].cpu().numpy(), t32[l].cpu().numpy()) <= 1e-5, (H, W, scale, l)
+            assert corr_err(f16[l].cpu().numpy(), ref[l].cpu().numpy()) <= 1e-3
+    z = torch.zeros(1, 256, 24, 32, device=cuda_device)
+    for lvl in cf.build_pyramid(z, dev_t(synth.corr_inputs(1, 192, 256, 1)[1], cuda_device), 4, precision="f16"):
+        assert not lvl.any()
+
+
 def test_corr_pair_kernel_subprocess(cuda_device):
     """The cta_group::2 variant of the tensor-core correlation (CF_TC_FLAGS bit6, read once per process, hence the
     subprocess): 256-row UMMAs across a CTA pair.  Checked against the fp32 SIMT kernel at an even tile count
