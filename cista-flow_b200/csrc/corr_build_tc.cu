@@ -91,6 +91,7 @@ struct Params {
                    //    9-12 per-atom boxes per stage made that issue rate the bound of the main loop (timeline)
     float *l0;
     float *l1;
+    int l1_staged;           // 1: level-1 rows are transposed through shared memory into 64-byte runs (w1 % 4 == 0)
     int lsu_stores;          // 1: level-0 rows leave through the LSU (transposed in shared memory), 0: TMA bulk stores
     const float *inv_scale;  // F16 operands: [2*B] powers of two that undo the per-item operand scaling (else nullptr)
     // deep fusion (tiles of 8k whole target rows, i.e. feature maps up to 32 wide -- the 180x240 / DAVIS240 case):
@@ -659,7 +660,43 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             s += __uint_as_float(rc[2 * q + 1]) * scale;
                             o[q] = s * 0.25f;
                         }
-                        if (row_ok && !(p.ablate & 1)) {
+                        if (p.l1_staged && p.w1 - (xc >> 1) >= 8) {   // (a narrow last strip is not worth the round trip)
+                            // the lane's 16 values (64 B of ITS row) -> shared memory -> whole 64-byte runs, 8 rows per
+                            // store instruction (lane <-> row 8*it + lane/4, piece lane%4) instead of 32 rows x 16 B
+                            const int npool = min(16, p.w1 - (xc >> 1));
+                            float *stg = reinterpret_cast<float *>(my_epi);
+                            if (!p.lsu_stores && lane == 0) tma_store_wait_read<0>();   // the level-0 boxes have left the buffers
+                            __syncwarp();
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                *reinterpret_cast<float4 *>(stg + lane * 16 + 4 * ((q + (lane >> 1)) & 3)) =
+                                    make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                            __syncwarp();
+                            const int row0 = mb * BM + 32 * quarter;
+                            if (vec4_l1) {
+                                const int pc = lane & 3;
+#pragma unroll
+                                for (int it = 0; it < 4; ++it) {
+                                    const int rr = 8 * it + (lane >> 2);
+                                    const float4 val = *reinterpret_cast<const float4 *>(stg + rr * 16 + 4 * ((pc + (rr >> 1)) & 3));
+                                    if (row0 + rr < p.N && 4 * pc < npool && !(p.ablate & 1))
+                                        *reinterpret_cast<float4 *>(p.l1 + ((size_t)b * p.N + row0 + rr) * p.h1 * p.w1 +
+                                                                    (size_t)(y >> 1) * p.w1 + (xc >> 1) + 4 * pc) = val;
+                                }
+                            } else {   // w1 even but not a multiple of 4: rows are only 8-byte aligned -> float2 pieces, 4 rows per store
+                                const int pc = lane & 7;
+#pragma unroll
+                                for (int it = 0; it < 8; ++it) {
+                                    const int rr = 4 * it + (lane >> 3);
+                                    const float2 val = *reinterpret_cast<const float2 *>(
+                                        stg + rr * 16 + 4 * (((pc >> 1) + (rr >> 1)) & 3) + 2 * (pc & 1));
+                                    if (row0 + rr < p.N && 2 * pc < npool && !(p.ablate & 1))
+                                        *reinterpret_cast<float2 *>(p.l1 + ((size_t)b * p.N + row0 + rr) * p.h1 * p.w1 +
+                                                                    (size_t)(y >> 1) * p.w1 + (xc >> 1) + 2 * pc) = val;
+                                }
+                            }
+                            __syncwarp();
+                        } else if (row_ok && !(p.ablate & 1)) {
                             float *dst = l1map + (size_t)(y >> 1) * p.w1 + (xc >> 1);
                             const int npool = min(16, p.w1 - (xc >> 1));
                             if (vec4_l1) {
@@ -688,20 +725,37 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                 const int r2g = r1g >> 1;
                                 if (row_ok && r2g < p.h2 && !(p.ablate & 1)) {
                                     float *d2 = p.l2 + (((size_t)b * p.N + i) * p.h2 + r2g) * p.w2;   // w2 is even
+                                    if ((p.w2 & 3) == 0) {   // 16-byte aligned rows: w2 = 4 or 8
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q)
-                                        if (2 * q < p.w2) *(reinterpret_cast<float2 *>(d2) + q) = make_float2(l2v[2 * q], l2v[2 * q + 1]);
+                                        for (int q = 0; q < 2; ++q)
+                                            if (4 * q < p.w2)
+                                                *(reinterpret_cast<float4 *>(d2) + q) = make_float4(l2v[4 * q], l2v[4 * q + 1], l2v[4 * q + 2], l2v[4 * q + 3]);
+                                    } else {
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q)
+                                            if (2 * q < p.w2) *(reinterpret_cast<float2 *>(d2) + q) = make_float2(l2v[2 * q], l2v[2 * q + 1]);
+                                    }
                                 }
                                 if (p.deep > 1) {
                                     if (r2g & 1) {
                                         const int r3g = r2g >> 1;
+                                        float l3v[4];
 #pragma unroll
                                         for (int q = 0; q < 4; ++q) {
                                             float s3 = prev2[2 * q] + prev2[2 * q + 1];
                                             s3 += l2v[2 * q];
                                             s3 += l2v[2 * q + 1];
-                                            if (row_ok && r3g < p.h3 && q < p.w3 && !(p.ablate & 1))
-                                                p.l3[(((size_t)b * p.N + i) * p.h3 + r3g) * p.w3 + q] = s3 * 0.25f;
+                                            l3v[q] = s3 * 0.25f;
+                                        }
+                                        if (row_ok && r3g < p.h3 && !(p.ablate & 1)) {
+                                            float *d3 = p.l3 + (((size_t)b * p.N + i) * p.h3 + r3g) * p.w3;
+                                            if (p.w3 == 4 && (reinterpret_cast<uintptr_t>(p.l3) & 15u) == 0) {
+                                                *reinterpret_cast<float4 *>(d3) = make_float4(l3v[0], l3v[1], l3v[2], l3v[3]);
+                                            } else {
+#pragma unroll
+                                                for (int q = 0; q < 4; ++q)
+                                                    if (q < p.w3) d3[q] = l3v[q];
+                                            }
                                         }
                                     } else {
 #pragma unroll
@@ -988,6 +1042,9 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // level-0 rows through the LSU instead of TMA bulk stores: helps where the operand loads already need many TMA
     // instructions per stage (N % 32 != 0: 64 x 36x44 398 -> 367 us), costs 2-5 % elsewhere (flags bit0: always TMA)
     p.lsu_stores = (!(flags & 1) && !p.atoms3d && N % 4 == 0) ? 1 : 0;
+    // level-1 rows through shared memory into 64-byte runs (flags bit13: per-lane 16-byte stores): 64 x 24x32
+    // 66.7 -> 60.8 us, 8 x 60x80 314 -> 309 us
+    p.l1_staged = (p.R > 0 && p.w1 % 2 == 0 && !(flags & 8192)) ? 1 : 0;
     p.tiles_mp = (int)ceil_div(p.tiles_m, 2);
     p.b_half = (int)ceil_div(p.BN_mma / 2, 32);
     if (pair) {
