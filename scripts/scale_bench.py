@@ -75,6 +75,19 @@ def tile_windows(ev, off, B):
     return evs[:offs[-1]], offs
 
 
+def _maybe_set_l2_fetch_granularity():
+    """Experiment knob: CF_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity (0x05) for the process."""
+    g = os.environ.get("CF_L2_FETCH")
+    if g:
+        import ctypes
+        torch.zeros(1, device="cuda")
+        rt = ctypes.CDLL("libcudart.so.12")
+        err = rt.cudaDeviceSetLimit(ctypes.c_int(5), ctypes.c_size_t(int(g)))
+        val = ctypes.c_size_t(0)
+        rt.cudaDeviceGetLimit(ctypes.byref(val), ctypes.c_int(5))
+        print(f"cudaLimitMaxL2FetchGranularity <- {g}: err {err}, now {val.value}")
+
+
 def run_cases(cases, only, dev=None, verbose=True, voxel_paths=True):
     """Times the kernels named in `only` at the shapes named in `cases`; returns (rows, peaks)."""
     if dev is None:
@@ -164,6 +177,7 @@ def run_cases(cases, only, dev=None, verbose=True, voxel_paths=True):
 
 
 def main():
+    _maybe_set_l2_fetch_granularity()
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "scale_bench.json"))
     ap.add_argument("--only", default="voxel,warp,build,lookup")
