@@ -80,7 +80,7 @@ struct Params {
     int tiles_mp;  // pair kernel: pairs of query tiles per batch item (= ceil(tiles_m / 2)); total_tiles counts pairs
     int stages;      // shared-memory ring depth
     int stage_bytes; // A_BYTES + n_boxes_b * BOX_BYTES
-    int ablate;    // experiments (CF_TC_FLAGS bits 8-10): 1 = no level-0/1 stores, 2 = no MMAs, 4 = no operand loads, 8 = K-major instruction descriptor, 16 = no epilogue at all
+    int ablate;    // experiments (CF_TC_FLAGS bits 8-10): 1 = no level-0/1 stores, 2 = no MMAs, 4 = no operand loads, 8 = K-major instruction descriptor, 16 = no epilogue at all, 32 = no pooling part, 64 = no level-0 part
     int b_half;    // pair kernel: fmap2 boxes per stage and CTA (half of the tile's columns each)
     int h1, w1;    // level-1 map size
     float scale;
@@ -568,7 +568,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // ---- level 0: TMEM -> registers (x scale) -> swizzled smem box -> TMA bulk store.
             // A warp-wide st.global of this fragment would touch 32 different rows per instruction
             // (measured: 18k cycles per tile); the TMA writes whole 128-byte lines instead.
-            if (bn_valid >= 32) {
+            if (bn_valid >= 32 && !(p.ablate & 64)) {
                 const int nchunks = (bn_valid + 31) / 32;
                 for (int ci = half; ci < nchunks; ci += EPI_SPLIT) {
                     const int c0 = min(ci * 32, bn_valid - 32);  // last chunk overlaps its neighbour (same values)
@@ -637,7 +637,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             if (threadIdx.x == 0) TC_TRACE(tile_no, 13);
             // ---- level 1: 2x2 means straight from the accumulator rows
-            if (p.R != 0) {
+            if (p.R != 0 && !(p.ablate & 32)) {
                 const int y0 = nb * p.R;
                 float *l1map = p.l1 + ((size_t)b * p.N + (row_ok ? i : 0)) * p.h1 * p.w1;
                 float prev1[16], prev2[8];   // deep fusion: the previous level-1 / level-2 row of this query
@@ -1038,7 +1038,7 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // pairs of query tiles as one 256-row UMMA across two CTAs: measured slower than one CTA per tile on the B200
     // (8 x 60x80: 359 against 322 us, see the kernel's header), so only on request (flags bit6)
     const bool pair = (flags & 64) && p.tiles_m >= 2 && !f16;
-    p.ablate = (flags >> 8) & 31;
+    p.ablate = (flags >> 8) & 127;
     // level-0 rows through the LSU instead of TMA bulk stores: helps where the operand loads already need many TMA
     // instructions per stage (N % 32 != 0: 64 x 36x44 398 -> 367 us), costs 2-5 % elsewhere (flags bit0: always TMA)
     p.lsu_stores = (!(flags & 1) && !p.atoms3d && N % 4 == 0) ? 1 : 0;
