@@ -80,7 +80,7 @@ struct Params {
     int tiles_mp;  // pair kernel: pairs of query tiles per batch item (= ceil(tiles_m / 2)); total_tiles counts pairs
     int stages;      // shared-memory ring depth
     int stage_bytes; // A_BYTES + n_boxes_b * BOX_BYTES
-    int ablate;    // experiments (CF_TC_FLAGS bits 8-10): 1 = no level-0/1 stores, 2 = no MMAs, 4 = no operand loads, 8 = K-major instruction descriptor, 16 = no epilogue at all, 32 = no pooling part, 64 = no level-0 part
+    int ablate;    // experiments (CF_TC_FLAGS bits 8-10): 1 = no level-0/1 stores, 2 = no MMAs, 4 = no operand loads, 16 = no epilogue at all, 32 = no pooling part, 64 = no level-0 part
     int b_half;    // pair kernel: fmap2 boxes per stage and CTA (half of the tile's columns each)
     int h1, w1;    // level-1 map size
     float scale;
@@ -253,6 +253,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, MN-major, 128B swizzle with 32B atoms (see file header)
@@ -288,17 +298,6 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
-}
-// experiments only (ablate bit 8): canonical K-major 128B-swizzle descriptor over the same bytes (garbage results) --
-// times the MMA with the operand fetch pattern of a K-major layout
-__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(16u >> 4) << 16;
-    d |= (uint64_t)(1024u >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-    return d;
 }
 // instruction descriptor: D=f32, A=B=tf32, both MN-major, M=m (128, or 256 across a CTA pair), N=n
 __host__ __device__ inline uint32_t make_idesc_tf32(int n, int m = BM) {
@@ -487,45 +486,61 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp == MMA_WARP) {
         // -------------------------------------------------------------- MMA issuer
-        if (lane == 0 && rank == 0) {
+        // The WHOLE warp walks the loop (convergent, every value warp-uniform) and one elected lane issues: written as
+        // `if (lane == 0) { ... }` the compiler wrapped every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+        // sequence and rebuilt both 64-bit descriptors in front of it -- ~30 dependent uniform-datapath instructions
+        // per MMA, i.e. an issue interval of ~180 cycles for an MMA that occupies the tensor pipe for ~90.
+        if (rank == 0) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            uint32_t idesc = F16 ? make_idesc_f16(p.BN_mma) : make_idesc_tf32(p.BN_mma, CL * BM);
-            if (p.ablate & 8) idesc &= ~((1u << 15) | (1u << 16));  // experiment: K-major reads of the same bytes (garbage results)
+            const uint32_t idesc = F16 ? make_idesc_f16(p.BN_mma) : make_idesc_tf32(p.BN_mma, CL * BM);
+            // descriptor high words are constants of the layout; the low word = start address >> 4 | LBO << 16
+            const uint32_t desc_hi = F16 ? (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29))
+                                         : (uint32_t)((512u >> 4) | (1u << 14) | (1u << 29));
+            const uint32_t lbo_bits = (4096u >> 4) << 16;
+            const uint32_t smem_base = smem_u32(smem);
             int tile_no = 0;
             for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
                 tc_fence_after();
-                TC_TRACE(tile_no, 2);
+                if (lane == 0) TC_TRACE(tile_no, 2);
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    if (tile == first_tile && kb < 16) stamp(3 + kb);
-                    if (kb < 8) TC_TRACE(tile_no, 3 + kb);
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + ABYTES;
-#pragma unroll
-                    for (int kk = 0; kk < MMAS; ++kk) {
-                        if (p.ablate & 2) continue;
-                        if (F16) {
-                            umma_f16(d_tmem, make_desc_mn_f16(sa + kk * KSTEP), make_desc_mn_f16(sb + kk * KSTEP), idesc,
-                                     (uint32_t)((kb | kk) != 0));
-                            continue;
-                        }
-                        const uint64_t da = (p.ablate & 8) ? make_desc_k_sw128(sa + kk * 32) : make_desc_mn_sw128(sa + kk * KSTEP);
-                        const uint64_t db = (p.ablate & 8) ? make_desc_k_sw128(sb + kk * 32) : make_desc_mn_sw128(sb + kk * KSTEP);
-                        if (CL == 2) umma_tf32_2sm(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
-                        else umma_tf32(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
+                    if (lane == 0) {
+                        if (tile == first_tile && kb < 16) stamp(3 + kb);
+                        if (kb < 8) TC_TRACE(tile_no, 3 + kb);
                     }
-                    // frees the smem slot once these MMAs have read it (pair kernel: in both CTAs)
-                    if (CL == 2) umma_commit_2sm(&empty[stage], (uint16_t)3);
-                    else umma_commit(&empty[stage]);
+                    const uint32_t sa = smem_base + (uint32_t)(stage * STAGE_BYTES);
+                    const uint32_t a_lo = (((sa & 0x3FFFFu) >> 4) | lbo_bits), b_lo = ((((sa + ABYTES) & 0x3FFFFu) >> 4) | lbo_bits);
+                    if (elect_one()) {
+                        if (!(p.ablate & 2)) {
+#pragma unroll
+                            for (int kk = 0; kk < MMAS; ++kk) {
+                                const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)(kk * (KSTEP >> 4)));
+                                const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)(kk * (KSTEP >> 4)));
+                                if (F16) umma_f16(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
+                                else if (CL == 2) umma_tf32_2sm(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
+                                else umma_tf32(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
+                            }
+                        }
+                        // frees the smem slot once these MMAs have read it (pair kernel: in both CTAs)
+                        if (CL == 2) umma_commit_2sm(&empty[stage], (uint16_t)3);
+                        else umma_commit(&empty[stage]);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (CL == 2) umma_commit_2sm(&tfull[acc], (uint16_t)3);  // accumulator complete -> both epilogues
-                else umma_commit(&tfull[acc]);
-                if (tile == first_tile) stamp(19);
-                TC_TRACE(tile_no, 11);
+                if (elect_one()) {
+                    if (CL == 2) umma_commit_2sm(&tfull[acc], (uint16_t)3);  // accumulator complete -> both epilogues
+                    else umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (tile == first_tile) stamp(19);
+                    TC_TRACE(tile_no, 11);
+                }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -1038,7 +1053,7 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // pairs of query tiles as one 256-row UMMA across two CTAs: measured slower than one CTA per tile on the B200
     // (8 x 60x80: 359 against 322 us, see the kernel's header), so only on request (flags bit6)
     const bool pair = (flags & 64) && p.tiles_m >= 2 && !f16;
-    p.ablate = (flags >> 8) & 127;
+    p.ablate = (flags >> 8) & 255;
     // level-0 rows through the LSU instead of TMA bulk stores: helps where the operand loads already need many TMA
     // instructions per stage (N % 32 != 0: 64 x 36x44 398 -> 367 us), costs 2-5 % elsewhere (flags bit0: always TMA)
     p.lsu_stores = (!(flags & 1) && !p.atoms3d && N % 4 == 0) ? 1 : 0;
