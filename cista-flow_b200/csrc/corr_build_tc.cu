@@ -427,7 +427,10 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     if (warp == PRODUCER_WARP) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // (whole warp convergent, an elected lane issues -- see the MMA issuer below: under `if (lane == 0)` every
+        //  cp.async.bulk.tensor cost an ELECT / R2UR / BRA.U.ANY sequence, the "one TMA issue per ~100 cycles" measured
+        //  earlier)
+        {
             int stage = 0;
             uint32_t phase = 0;
             // pair kernel: the leader's barrier counts the bytes of BOTH CTAs' boxes
@@ -441,15 +444,24 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int i0 = mb * BM, j0 = nb * p.BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    if (kb == 0) TC_TRACE(tile_no, 0);
-                    if (kb == kblocks - 1) TC_TRACE(tile_no, 1);
+                    if (lane == 0) {
+                        if (kb == 0) TC_TRACE(tile_no, 0);
+                        if (kb == kblocks - 1) TC_TRACE(tile_no, 1);
+                    }
                     uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + ABYTES;
-                    if (p.ablate & 4) {
-                        if (rank == 0) mbar_arrive(&full[stage]);
+                    const int krow = b * p.D + kb * BK;
+                    const bool issuer = elect_one();
+                    if (!issuer) {
+                        __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
-                    const int krow = b * p.D + kb * BK;
+                    if (p.ablate & 4) {
+                        if (rank == 0) mbar_arrive(&full[stage]);
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (CL == 2) {
                         if (rank == 0) mbar_expect_tx(&full[stage], tx_bytes);
                         const uint32_t lead_full = mapa_rank0(&full[stage]);
@@ -464,6 +476,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         } else {
                             for (int a = 0; a < p.b_half; ++a) tma_load_2d_2sm(sb + a * BOX_BYTES, &tmap_b, j0 + jr + 32 * a, krow, lead_full);
                         }
+                        __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
@@ -480,6 +493,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOX_BYTES, &tmap_b, j0 + BC * a, krow, &full[stage]);
                     }
                     if (tile == first_tile && kb == 0) stamp(2);
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
