@@ -263,10 +263,8 @@ static int launch_lookup_r4l4(const Pyramid &pyr, const float *coords, float *ou
             if (best < 0 || cost < best) { best = cost; qt = cand; }
         }
     }
-    if (const char *force = getenv("CF_LOOKUP_QT")) {  // experiments
-        const int f = atoi(force);
-        if (f >= 2 && f <= 32 && (f & 1) == 0) qt = f;
-    }
+    static const int forced_qt = [] { const char *e = getenv("CF_LOOKUP_QT"); return e ? atoi(e) : 0; }();  // experiments
+    if (forced_qt >= 2 && forced_qt <= 32 && (forced_qt & 1) == 0) qt = forced_qt;
     const size_t smem = (size_t)qt * 401 * sizeof(float);
     int dev = 0;
     CF_CUDA(cudaGetDevice(&dev));
