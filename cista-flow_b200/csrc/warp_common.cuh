@@ -104,25 +104,49 @@ __device__ __forceinline__ void warp_pixel(const float *__restrict__ img_b, floa
     const size_t pb = plane * sizeof(float);
     const char *src = reinterpret_cast<const char *>(img_b) + (size_t)c0 * pb;
     char *dst = reinterpret_cast<char *>(out_b) + (size_t)c0 * pb;
-    float v[CPT][4];
+    if (c0 + CPT <= C) {   // whole batch of channels in range: no per-channel predicates (the common case, C % CPT == 0)
+        float v[CPT][4];
+        if (b01 == b00 + 4u && b11 == b10 + 4u) {
+            // the right-hand taps are the next float (everywhere but on the clamped last column): two addresses per
+            // channel, the +4 rides in the load's immediate offset
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        if (c0 + k < C) {
-            const char *s = src + (size_t)k * pb;
-            v[k][0] = __ldg(reinterpret_cast<const float *>(s + b00));
-            v[k][1] = __ldg(reinterpret_cast<const float *>(s + b01));
-            v[k][2] = __ldg(reinterpret_cast<const float *>(s + b10));
-            v[k][3] = __ldg(reinterpret_cast<const float *>(s + b11));
+            for (int k = 0; k < CPT; ++k) {
+                const float *top = reinterpret_cast<const float *>(src + (size_t)k * pb + b00);
+                const float *bot = reinterpret_cast<const float *>(src + (size_t)k * pb + b10);
+                v[k][0] = __ldg(top);
+                v[k][1] = __ldg(top + 1);
+                v[k][2] = __ldg(bot);
+                v[k][3] = __ldg(bot + 1);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const char *s = src + (size_t)k * pb;
+                v[k][0] = __ldg(reinterpret_cast<const float *>(s + b00));
+                v[k][1] = __ldg(reinterpret_cast<const float *>(s + b01));
+                v[k][2] = __ldg(reinterpret_cast<const float *>(s + b10));
+                v[k][3] = __ldg(reinterpret_cast<const float *>(s + b11));
+            }
         }
-    }
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        if (c0 + k < C) {
+        for (int k = 0; k < CPT; ++k) {
             // ATen order: nw, ne, sw, se accumulated left to right
             float r = v[k][0] * t.w00;
             r += v[k][1] * t.w01;
             r += v[k][2] * t.w10;
             r += v[k][3] * t.w11;
+            st_cs(reinterpret_cast<float *>(dst + (size_t)k * pb + bo), r);
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        if (c0 + k < C) {
+            const char *s = src + (size_t)k * pb;
+            float r = __ldg(reinterpret_cast<const float *>(s + b00)) * t.w00;
+            r += __ldg(reinterpret_cast<const float *>(s + b01)) * t.w01;
+            r += __ldg(reinterpret_cast<const float *>(s + b10)) * t.w10;
+            r += __ldg(reinterpret_cast<const float *>(s + b11)) * t.w11;
             st_cs(reinterpret_cast<float *>(dst + (size_t)k * pb + bo), r);
         }
     }
