@@ -50,8 +50,50 @@ constexpr int CH_PER_CTA = 64;           // channel group of one CTA (8 stages o
                                          // against 141 us (73 %); 128: 162 / 145 us
 }  // namespace wt
 
+// One 32x32 block of the (few-channel, full-resolution) image: thread <-> 4 rows; all flow loads, then all 16 tap
+// loads, then the stores (one pixel per thread cost two dependent DRAM round trips per 256 pixels).
+__device__ __forceinline__ void warp_image_block(const WarpJob &ji, const float *__restrict__ flow, int fH, int fW, float sign,
+                                                 bool identity, int b, int bx0, int by0) {
+    const int Hi = ji.H, Wi = ji.W;
+    const size_t hw = (size_t)Hi * Wi;
+    const float *fbi = flow + (size_t)b * 2 * fH * fW;  // image resolution == flow resolution
+    const int x = bx0 + (int)(threadIdx.x & 31);
+    const int xc = min(x, Wi - 1);
+    int yy[4];
+    float fu[4], fv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        yy[k] = by0 + (int)(threadIdx.x >> 5) + 8 * k;
+        const int yc = min(yy[k], Hi - 1);
+        fu[k] = __ldg(fbi + (size_t)yc * Wi + xc);
+        fv[k] = __ldg(fbi + hw + (size_t)yc * Wi + xc);
+    }
+    Taps t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        t[k] = identity ? identity_taps(xc, min(yy[k], Hi - 1), Wi) : make_taps(fu[k], fv[k], xc, min(yy[k], Hi - 1), Hi, Wi, sign);
+    for (int c = 0; c < ji.C; ++c) {
+        const float *src = ji.img + ((size_t)b * ji.C + c) * hw;
+        float *dst = ji.out + ((size_t)b * ji.C + c) * hw;
+        float v[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k][0] = __ldg(src + t[k].o00); v[k][1] = __ldg(src + t[k].o01);
+            v[k][2] = __ldg(src + t[k].o10); v[k][3] = __ldg(src + t[k].o11);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float r = v[k][0] * t[k].w00;
+            r += v[k][1] * t[k].w01;
+            r += v[k][2] * t[k].w10;
+            r += v[k][3] * t[k].w11;
+            if (x < Wi && yy[k] < Hi) st_cs(dst + (size_t)yy[k] * Wi + x, r);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256, 3)
-warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_blocks, WarpJob jz, int tiles_x, int tiles,
+warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_in_tiles, WarpJob jz, int tiles_x, int tiles,
                 int groups, const float *__restrict__ flow, int fH, int fW, float sign, const int *__restrict__ gate) {
     using namespace wt;
     const bool identity = gate_closed(gate);  // device-side `not flow_final.any()` (e2v_model.py:184): copy
@@ -59,52 +101,24 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int n_img_
     int blk = blockIdx.x;
     const int n_codes_blocks = tiles * groups;
     if (blk >= n_codes_blocks) {
-        // image part (after the codes blocks in launch order: it fills the partial last wave).  One CTA =
-        // a 32x32 pixel region, thread <-> 4 rows: all flow loads, then all 16 tap loads, then the stores
-        // (one pixel per thread cost two dependent DRAM round trips per 256 pixels: 8 of 32 us at 180x240)
+        // image part as CTAs of its own (after the codes blocks in launch order; only when it cannot ride inside the
+        // codes tiles, see below): one CTA = a 32x32 pixel block
         blk -= n_codes_blocks;
         const int itx = (ji.W + 31) / 32;
         const int ity = blk / itx, itxx = blk - ity * itx;
-        const int Hi = ji.H, Wi = ji.W;
-        const size_t hw = (size_t)Hi * Wi;
-        const float *fbi = flow + (size_t)b * 2 * fH * fW;  // image resolution == flow resolution
-        const int x = itxx * 32 + (threadIdx.x & 31);
-        const int xc = min(x, Wi - 1);
-        int yy[4];
-        float fu[4], fv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            yy[k] = ity * 32 + (int)(threadIdx.x >> 5) + 8 * k;
-            const int yc = min(yy[k], Hi - 1);
-            fu[k] = __ldg(fbi + (size_t)yc * Wi + xc);
-            fv[k] = __ldg(fbi + hw + (size_t)yc * Wi + xc);
-        }
-        Taps t[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            t[k] = identity ? identity_taps(xc, min(yy[k], Hi - 1), Wi) : make_taps(fu[k], fv[k], xc, min(yy[k], Hi - 1), Hi, Wi, sign);
-        for (int c = 0; c < ji.C; ++c) {
-            const float *src = ji.img + ((size_t)b * ji.C + c) * hw;
-            float *dst = ji.out + ((size_t)b * ji.C + c) * hw;
-            float v[4][4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                v[k][0] = __ldg(src + t[k].o00); v[k][1] = __ldg(src + t[k].o01);
-                v[k][2] = __ldg(src + t[k].o10); v[k][3] = __ldg(src + t[k].o11);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float r = v[k][0] * t[k].w00;
-                r += v[k][1] * t[k].w01;
-                r += v[k][2] * t[k].w10;
-                r += v[k][3] * t[k].w11;
-                if (x < Wi && yy[k] < Hi) st_cs(dst + (size_t)yy[k] * Wi + x, r);
-            }
-        }
+        warp_image_block(ji, flow, fH, fW, sign, identity, b, itxx * 32, ity * 32);
         return;
     }
     const int group = blk / tiles, tile = blk - group * tiles;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    // image_in_tiles: the first channel group's CTA of a codes tile (32x16 at half resolution) also warps the 64x32
+    // full-resolution image pixels over that tile, before its own work: as CTAs of their own the image blocks were
+    // held to this kernel's 3 CTAs per SM by its shared-memory footprint and ran as a latency-bound tail (8x480x640:
+    // fused 147 us against 130 us for the codes alone)
+    if (image_in_tiles && group == 0) {
+        warp_image_block(ji, flow, fH, fW, sign, identity, b, 64 * tx, 32 * ty);
+        warp_image_block(ji, flow, fH, fW, sign, identity, b, 64 * tx + 32, 32 * ty);
+    }
 
     // declared aligned, no run-time rounding: keeps the pointers in the shared address space (LDS, not generic LD.E)
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -268,9 +282,17 @@ int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const
     }
     const int tiles_x = (int)ceil_div(jz.W, TW), tiles = tiles_x * (int)ceil_div(jz.H, TH);
     const int groups = (int)ceil_div(jz.C, CH_PER_CTA);
-    const int n_img = with_image ? (int)(ceil_div(ji.W, 32) * ceil_div(ji.H, 32)) : 0;
+    // even image sizes (the reference requires them, data_readers/video_readers.py:403-404): the 64x32 image pixels over
+    // a codes tile are exactly that tile's share; odd sizes keep separate image CTAs
+    static const char *env_img = getenv("CF_WARP_IMAGE_CTAS");   // experiments: "1" forces separate image CTAs
+    // ... and only when the codes tiles run in several waves (64x180x240: 160 -> 156 us, 8x480x640: 141 -> 137 us): in a
+    // single wave the longer first-group CTAs are the critical path (8x180x240: 27.7 against 26.5 us)
+    const int64_t code_ctas = (int64_t)ceil_div(jz.W, TW) * ceil_div(jz.H, TH) * ceil_div(jz.C, CH_PER_CTA) * B;
+    const bool in_tiles = with_image && ji.H == 2 * jz.H && ji.W == 2 * jz.W && code_ctas > 6 * (int64_t)sm_count() &&
+                          !(env_img && !strcmp(env_img, "1"));
+    const int n_img = (with_image && !in_tiles) ? (int)(ceil_div(ji.W, 32) * ceil_div(ji.H, 32)) : 0;
     dim3 grid((unsigned)(n_img + tiles * groups), (unsigned)B);
-    warp_tma_kernel<<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, n_img, jz, tiles_x, tiles, groups, flow, fH, fW, sign, gate);
+    warp_tma_kernel<<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, in_tiles ? 1 : 0, jz, tiles_x, tiles, groups, flow, fH, fW, sign, gate);
     CF_LAUNCH_CHECK("warp_tma_kernel");
     return CF_OK;
 }

@@ -311,6 +311,24 @@ def test_warp_staged_paths_smooth_flow(cuda_device, h, w, batch, channels, kerne
     assert (got.cpu() - ref_z).abs().max().item() <= 1e-4
 
 
+def test_warp_image_rides_in_the_codes_tiles(cuda_device):
+    """Many codes tiles (several waves of CTAs): the image blocks are warped by the first channel group's CTA of each
+    codes tile instead of CTAs of their own.  24 streams of 192x256 with 128-channel codes = 1152 codes CTAs; both
+    outputs against the oracle, including a frame whose flow has a discontinuity (direct-gather fallback tiles) and
+    the gated all-zero-flow copy."""
+    B, C, H, W = 24, 128, 192, 256
+    img, codes, flow = synth.warp_inputs(B, H, W, seed=21, code_channels=C, flow_kind="smooth")
+    flow[3, :, 50:120, 80:170] += 41.0
+    ref_i, ref_z = ref_port.warp_frame_and_codes(torch.from_numpy(img), torch.from_numpy(codes), torch.from_numpy(flow), "forward")
+    di, dz, df = dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(flow, cuda_device)
+    wi, wz = cf.warp_frame_and_codes(di, dz, df, "forward")
+    assert last_kernel() == "warp_tma_kernel"
+    assert (wi.cpu() - ref_i).abs().max().item() <= 1e-4
+    assert (wz.cpu() - ref_z).abs().max().item() <= 1e-4
+    gi, gz = cf.warp_frame_and_codes(di, dz, torch.zeros_like(df), "forward", skip_zero_flow=True)
+    assert torch.equal(gi, di) and torch.equal(gz, dz)
+
+
 def test_warp_staged_misaligned_base_and_mixed_tiles(cuda_device):
     """(a) a codes tensor whose base address is only 4-byte aligned (a view into a larger buffer) cannot
     be described by a tensor map and takes the direct gather; (b) smooth flow with one discontinuity: tiles
