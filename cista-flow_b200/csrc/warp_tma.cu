@@ -100,24 +100,31 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
     const int b = blockIdx.y;
     int blk = blockIdx.x;
     const int n_codes_blocks = tiles * groups;
-    if (blk >= n_codes_blocks) {
-        // image part as CTAs of its own (after the codes blocks in launch order; only when it cannot ride inside the
-        // codes tiles, see below): one CTA = a 32x32 pixel block
-        blk -= n_codes_blocks;
-        const int itx = (ji.W + 31) / 32;
-        const int ity = blk / itx, itxx = blk - ity * itx;
-        warp_image_block(ji, flow, fH, fW, sign, identity, b, itxx * 32, ity * 32);
-        return;
-    }
-    const int group = blk / tiles, tile = blk - group * tiles;
+    // Image part.  Either CTAs of their own after the codes blocks in launch order (one 32x32 pixel block each), or --
+    // image_in_tiles -- the first channel group's CTA of a codes tile (32x16 at half resolution) also warps the 64x32
+    // full-resolution image pixels over that tile, before its own work: as CTAs of their own the image blocks are held
+    // to this kernel's 3 CTAs per SM by its shared-memory footprint and run as a latency-bound tail (8x480x640: fused
+    // 147 us against 130 us for the codes alone).  ONE copy of the block code serves both (a second and third inlined
+    // copy cost 7 us per step at configs[1] through the instruction cache).
+    const bool image_cta = blk >= n_codes_blocks;
+    const int cblk = image_cta ? 0 : blk;
+    const int group = cblk / tiles, tile = cblk - group * tiles;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    // image_in_tiles: the first channel group's CTA of a codes tile (32x16 at half resolution) also warps the 64x32
-    // full-resolution image pixels over that tile, before its own work: as CTAs of their own the image blocks were
-    // held to this kernel's 3 CTAs per SM by its shared-memory footprint and ran as a latency-bound tail (8x480x640:
-    // fused 147 us against 130 us for the codes alone)
-    if (image_in_tiles && group == 0) {
-        warp_image_block(ji, flow, fH, fW, sign, identity, b, 64 * tx, 32 * ty);
-        warp_image_block(ji, flow, fH, fW, sign, identity, b, 64 * tx + 32, 32 * ty);
+    {
+        int n_blocks = 0, bx0 = 0, by0 = 0;
+        if (image_cta) {
+            const int iblk = blk - n_codes_blocks, itx = (ji.W + 31) / 32;
+            n_blocks = 1;
+            by0 = (iblk / itx) * 32;
+            bx0 = (iblk - (iblk / itx) * itx) * 32;
+        } else if (image_in_tiles && group == 0) {
+            n_blocks = 2;
+            bx0 = 64 * tx;
+            by0 = 32 * ty;
+        }
+#pragma unroll 1
+        for (int k = 0; k < n_blocks; ++k) warp_image_block(ji, flow, fH, fW, sign, identity, b, bx0 + 32 * k, by0);
+        if (image_cta) return;
     }
 
     // declared aligned, no run-time rounding: keeps the pointers in the shared address space (LDS, not generic LD.E)
