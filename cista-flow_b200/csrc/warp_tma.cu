@@ -92,6 +92,31 @@ __device__ __forceinline__ void warp_image_block(const WarpJob &ji, const float 
     }
 }
 
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ bool elect_lane() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
+// QUAD: tensors without a 16-byte row pitch (W % 4 != 0, e.g. the 130x173 codes of a 260x346 sensor).  No tensor map
+// can describe their rows, but the whole buffer seen as a matrix of 4*W floats per row -- four source rows side by side,
+// pitch 16*W bytes -- can: a [48 x 6] box at column (g % 4)*W + x0, map row g/4 is source rows g, g+4, .., g+20 (g = the
+// global source-row index (b*C + c)*H + y).  Four boxes (g = g0 .. g0+3, g0 the row of the tile's first source row) per
+// channel bring its 24 source rows, which land residue-major: row g0 + k sits in shared row (k % 4)*6 + k/4.  But
+//   * the box column must be a multiple of 4 floats (a start coordinate that is not 16-byte aligned raises "illegal
+//     instruction" on the B200 -- scripts/experiments/quad_probe.cu), so a box starts at ((g % 4)*W + x0) & ~3 and its
+//     data sits ((g % 4)*W + x0) % 4 floats further right: the usable box is 45 columns;
+//   * that shift depends on q = g0 % 4, hence on the channel through c*H % 4.  A stage therefore holds 8 channels of
+//     one residue class -- channel stride P = 1, 2 or 4 for H % 4 == 0, H even, H odd -- so that q is uniform per stage
+//     and the tap offsets are recomputed per stage (a few integer operations), not per channel.
+// Each warp's elected lane issues the four boxes of one channel (32 instructions per stage from one thread would
+// serialise behind its own gather work).
+template <bool QUAD>
 __global__ void __launch_bounds__(256, 3)
 warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_in_tiles, WarpJob jz, int tiles_x, int tiles,
                 int groups, const float *__restrict__ flow, int fH, int fW, float sign, const int *__restrict__ gate) {
@@ -146,7 +171,9 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
     bool live[2];
     int x0a[2], y0a[2];
     int mnx = INT_MAX, mny = INT_MAX, mxx = -1, mxy = -1;
-    const int y = ty * TH + 2 * warp + (lane >> 4);
+    // QUAD: the two half-warps sit 4 rows apart -- shared rows rr and rr + 4 are neighbours (16 banks apart), rr and
+    // rr + 1 are 6 rows = 0 banks apart
+    const int y = ty * TH + (QUAD ? (warp & 3) + 8 * (warp >> 2) + 4 * (lane >> 4) : 2 * warp + (lane >> 4));
     const int xl = tx * TW + (lane & 15);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -175,19 +202,19 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
     }
     if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mxx; red[3][warp] = mxy; }
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], QUAD ? 8 : 1);
         ptx::fence_barrier_init();
     }
     __syncthreads();
     if (tid == 0) {
         int a = INT_MAX, c = INT_MAX, d = -1, e = -1;
         for (int k = 0; k < 8; ++k) { a = min(a, red[0][k]); c = min(c, red[1][k]); d = max(d, red[2][k]); e = max(e, red[3][k]); }
-        s_box[0] = a & ~3;  // 16-byte aligned box origin: keeps the TMA requests sector-aligned
+        s_box[0] = QUAD ? a : a & ~3;  // 16-byte aligned box origin: keeps the TMA requests sector-aligned
         s_box[1] = c; s_box[2] = d; s_box[3] = e;
     }
     __syncthreads();
     const int bx = s_box[0], by = s_box[1];
-    const bool fits = s_box[2] >= 0 && (s_box[2] - bx) < BW && (s_box[3] - by) < BH;
+    const bool fits = s_box[2] >= 0 && (s_box[2] - bx) < (QUAD ? BW - 3 : BW) && (s_box[3] - by) < BH;
 
     const int c_begin = group * CH_PER_CTA, c_end = min(jz.C, c_begin + CH_PER_CTA);
     const size_t plane = (size_t)H * W;
@@ -210,35 +237,65 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
     for (int k = 0; k < 2; ++k) {
         if (live[k]) {
             const int x1 = taps[k].o01 - y0a[k] * W, y1 = taps[k].o10 / W;
-            s00[k] = (y0a[k] - by) * BW + (x0a[k] - bx);
-            s01[k] = (y0a[k] - by) * BW + (x1 - bx);
-            s10[k] = (y1 - by) * BW + (x0a[k] - bx);
-            s11[k] = (y1 - by) * BW + (x1 - bx);
+            const int r0 = y0a[k] - by, r1 = y1 - by;
+            if (QUAD) {  // row and column kept apart: the shared-memory row depends on the stage's q
+                s00[k] = r0; s01[k] = x0a[k] - bx; s10[k] = r1; s11[k] = x1 - bx;
+            } else {
+                s00[k] = r0 * BW + (x0a[k] - bx);
+                s01[k] = r0 * BW + (x1 - bx);
+                s10[k] = r1 * BW + (x0a[k] - bx);
+                s11[k] = r1 * BW + (x1 - bx);
+            }
         }
     }
 
     const int nchunks = (c_end - c_begin + CC - 1) / CC;
-    if (tid == 0) {
-        for (int k = 0; k < STAGES - 1 && k < nchunks; ++k) {
-            ptx::mbar_expect_tx(&full[k], STAGE_BYTES);
-            ptx::tma_load_4d(stage0 + k * STAGE_FLOATS, &tmap, bx, by, c_begin + k * CC, b, &full[k]);
+    // QUAD: stage `chunk` holds channels first_channel(chunk) + P*i, i = 0..7 (the group's channel count is a multiple of
+    // 8*P); warp <-> channel i of the stage
+    const int P = QUAD ? ((H & 3) == 0 ? 1 : ((H & 1) ? 4 : 2)) : 1;
+    auto first_channel = [&](int chunk) { return c_begin + (chunk % P) + P * CC * (chunk / P); };
+    auto issue = [&](int chunk) {
+        float *dst = stage0 + (chunk % STAGES) * STAGE_FLOATS;
+        uint64_t *bar = &full[chunk % STAGES];
+        if (QUAD) {
+            __syncwarp();
+            if (elect_lane()) {
+                ptx::mbar_expect_tx(bar, STAGE_BYTES / CC);
+                const int g0 = (b * jz.C + first_channel(chunk) + P * warp) * H + by;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int g = g0 + j;
+                    tma_load_2d(dst + (warp * BH + j * (BH / 4)) * BW, &tmap, ((g & 3) * W + bx) & ~3, g >> 2, bar);
+                }
+            }
+            __syncwarp();
+        } else if (tid == 0) {
+            ptx::mbar_expect_tx(bar, STAGE_BYTES);
+            ptx::tma_load_4d(dst, &tmap, bx, by, c_begin + chunk * CC, b, bar);
         }
-    }
+    };
+    for (int k = 0; k < STAGES - 1 && k < nchunks; ++k) issue(k);
     for (int k = 0; k < nchunks; ++k) {
         const int nxt = k + STAGES - 1;
-        if (tid == 0 && nxt < nchunks) {  // slot (nxt % STAGES) was drained at the end of iteration k-1
-            ptx::mbar_expect_tx(&full[nxt % STAGES], STAGE_BYTES);
-            ptx::tma_load_4d(stage0 + (nxt % STAGES) * STAGE_FLOATS, &tmap, bx, by, c_begin + nxt * CC, b, &full[nxt % STAGES]);
-        }
+        if (nxt < nchunks) issue(nxt);  // slot (nxt % STAGES) was drained at the end of iteration k-1
         ptx::mbar_wait(&full[k % STAGES], (uint32_t)((k / STAGES) & 1));
         const float *st = stage0 + (k % STAGES) * STAGE_FLOATS;
-        const int c0 = c_begin + k * CC;
-        const bool full_chunk = c0 + CC <= c_end;
+        const int c0 = QUAD ? first_channel(k) : c_begin + k * CC;
+        const bool full_chunk = QUAD || c0 + CC <= c_end;
+        const int q = QUAD ? (((b * jz.C + c0) * H + by) & 3) : 0;
+        const size_t ostep = QUAD ? (size_t)P * plane : plane;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             if (!live[j]) continue;
             float *o = out_b + (size_t)c0 * plane + (size_t)y * W + xl + 16 * j;
-            const float *s0 = st + s00[j], *s1 = st + s01[j], *s2 = st + s10[j], *s3 = st + s11[j];
+            int a0 = s00[j], a1 = s01[j], a2 = s10[j], a3 = s11[j];
+            if (QUAD) {  // row g0 + k -> shared row (k%4)*6 + k/4, shifted right by (((g0 + k) % 4)*W + x0) % 4
+                const int k0 = s00[j], k1 = s10[j];
+                const int row0 = ((k0 & 3) * (BH / 4) + (k0 >> 2)) * BW + ((((k0 + q) & 3) * W + bx) & 3);
+                const int row1 = ((k1 & 3) * (BH / 4) + (k1 >> 2)) * BW + ((((k1 + q) & 3) * W + bx) & 3);
+                a0 = row0 + s01[j]; a1 = row0 + s11[j]; a2 = row1 + s01[j]; a3 = row1 + s11[j];
+            }
+            const float *s0 = st + a0, *s1 = st + a1, *s2 = st + a2, *s3 = st + a3;
             const float w0 = taps[j].w00, w1 = taps[j].w01, w2 = taps[j].w10, w3 = taps[j].w11;
             float v[CC][4];  // all 32 tap loads before the first store (LDS/STG interleaving serialises on aliasing)
 #pragma unroll
@@ -255,7 +312,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
                 r += v[c][2] * w2;
                 r += v[c][3] * w3;
                 if (full_chunk || c0 + c < c_end) st_cs(o, r);
-                o += plane;
+                o += ostep;
             }
         }
         __syncthreads();  // every thread is done with this stage before it is refilled
@@ -267,24 +324,43 @@ int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const
     using namespace wt;
     static const char *env = getenv("CF_WARP_PATH");  // experiments: "direct" forces the plain gather
     const bool disabled = env && !strcmp(env, "direct");
-    if (disabled || jz.W % 4 != 0 || jz.C < CC || !aligned16(jz.img)) return 1;
+    if (disabled || jz.C < CC || !aligned16(jz.img)) return 1;
+    const bool quad = jz.W % 4 != 0;
+    const int64_t src_rows = (int64_t)B * jz.C * jz.H;
+    const char *env_quad = quad ? getenv("CF_WARP_QUAD") : nullptr;  // "0" keeps odd pitches on the direct path, "1" stages them at any size
+    // one wave of CTAs or less is latency-bound and the four-box stages land later than the direct gather's taps
+    // (1x260x346: 21.8 against 14.2 us)
+    const int64_t quad_ctas = (int64_t)ceil_div(jz.W, TW) * ceil_div(jz.H, TH) * ceil_div(jz.C, CH_PER_CTA) * B;
+    if (quad && (jz.C % (4 * CC) != 0 || jz.W < 16 || (quad_ctas < 3 * (int64_t)sm_count() && !(env_quad && !strcmp(env_quad, "1"))) || src_rows > INT_MAX || (env_quad && !strcmp(env_quad, "0")))) return 1;
     TensorMapEncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return 1;
     CUtensorMap tmap;
-    cuuint64_t dims[4] = {(cuuint64_t)jz.W, (cuuint64_t)jz.H, (cuuint64_t)jz.C, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)jz.W * 4, (cuuint64_t)jz.W * jz.H * 4, (cuuint64_t)jz.W * jz.H * jz.C * 4};
-    cuuint32_t box[4] = {BW, BH, CC, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(jz.img), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r;
+    if (quad) {
+        cuuint64_t dims[2] = {(cuuint64_t)jz.W * 4, (cuuint64_t)(src_rows / 4)};
+        cuuint64_t strides[1] = {(cuuint64_t)jz.W * 16};
+        cuuint32_t box[2] = {BW, BH / 4};
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(jz.img), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[4] = {(cuuint64_t)jz.W, (cuuint64_t)jz.H, (cuuint64_t)jz.C, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)jz.W * 4, (cuuint64_t)jz.W * jz.H * 4, (cuuint64_t)jz.W * jz.H * jz.C * 4};
+        cuuint32_t box[4] = {BW, BH, CC, 1};
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(jz.img), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_CUDA, "cuTensorMapEncodeTiled (warp) failed with CUresult %d", (int)r);
     int dev = 0;
     CF_CUDA(cudaGetDevice(&dev));
     static bool opt_in[64] = {};
     if (!opt_in[dev & 63]) {
-        CF_CUDA(cudaFuncSetAttribute(warp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CF_CUDA(cudaFuncSetAttribute(warp_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CF_CUDA(cudaFuncSetAttribute(warp_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CF_CUDA(cudaFuncSetAttribute(warp_tma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CF_CUDA(cudaFuncSetAttribute(warp_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CF_CUDA(cudaFuncSetAttribute(warp_tma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         opt_in[dev & 63] = true;
     }
     const int tiles_x = (int)ceil_div(jz.W, TW), tiles = tiles_x * (int)ceil_div(jz.H, TH);
@@ -299,7 +375,10 @@ int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const
                           !(env_img && !strcmp(env_img, "1"));
     const int n_img = (with_image && !in_tiles) ? (int)(ceil_div(ji.W, 32) * ceil_div(ji.H, 32)) : 0;
     dim3 grid((unsigned)(n_img + tiles * groups), (unsigned)B);
-    warp_tma_kernel<<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, in_tiles ? 1 : 0, jz, tiles_x, tiles, groups, flow, fH, fW, sign, gate);
+    if (quad)
+        warp_tma_kernel<true><<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, in_tiles ? 1 : 0, jz, tiles_x, tiles, groups, flow, fH, fW, sign, gate);
+    else
+        warp_tma_kernel<false><<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, in_tiles ? 1 : 0, jz, tiles_x, tiles, groups, flow, fH, fW, sign, gate);
     CF_LAUNCH_CHECK("warp_tma_kernel");
     return CF_OK;
 }

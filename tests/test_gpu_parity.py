@@ -286,16 +286,20 @@ def test_warp_vs_oracle_config_shapes(cuda_device, h, w, batch, channels, mode):
 
 @pytest.mark.parametrize("h,w,batch,channels,kernel", [
     (180, 240, 2, 128, "persist"),    # configs[1]: 90x120 codes, row pitch % 16 B == 0 -> TMA tensor boxes
-    (260, 346, 1, 128, "direct"),      # configs[2]: 130x173 codes, odd width: no 16-byte row pitch -> direct gather
-    (624, 970, 1, 24, "direct"),       # configs[3] shape (312x485 codes), fewer channels to bound the CPU oracle
+    (260, 346, 1, 128, "persist"),     # configs[2]: 130x173 codes, odd width: no 16-byte row pitch -> quad-row tensor map
+    (624, 970, 1, 32, "persist"),      # configs[3] shape (312x485 codes, odd width, H % 4 == 0), fewer channels to bound the CPU oracle
     (64, 96, 3, 13, "persist"),       # 13 channels: last chunk is partial (TMA zero-fills the missing channels)
-    (66, 102, 2, 11, "direct"),        # 33x51 codes: odd width AND plane % 4 != 0
+    (66, 102, 2, 11, "direct"),        # 33x51 codes: odd width and 11 channels (the quad-row view needs C % 32 == 0)
+    (66, 102, 2, 32, "persist"),       # 33x51 codes: odd width, odd height (channel stride 4 per stage), plane % 4 != 0
+    (70, 44, 3, 64, "persist"),        # 35x22 codes: rows of 88 bytes (8-byte pitch), box wider than the image
     (36, 40, 1, 8, "persist"),        # tile larger than the image
 ])
 @pytest.mark.parametrize("mode", ["forward", "backward"])
-def test_warp_staged_paths_smooth_flow(cuda_device, h, w, batch, channels, kernel, mode):
+def test_warp_staged_paths_smooth_flow(cuda_device, monkeypatch, h, w, batch, channels, kernel, mode):
     """Network-like (smooth) flow: the taps of a tile fit the staging box, so the TMA-staged
     kernel does the work (asserted through cf_last_kernel), not the direct gather."""
+    if kernel == "persist" and (w // 2) % 4:
+        monkeypatch.setenv("CF_WARP_QUAD", "1")   # odd pitch: staged at any size (by default only from one full wave of CTAs)
     img, codes, flow = synth.warp_inputs(batch, h, w, seed=9, code_channels=channels, flow_kind="smooth")
     ref_i, ref_z = ref_port.warp_frame_and_codes(torch.from_numpy(img), torch.from_numpy(codes), torch.from_numpy(flow), mode)
     wi, wz = cf.warp_frame_and_codes(dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(flow, cuda_device), mode)
@@ -326,6 +330,25 @@ def test_warp_image_rides_in_the_codes_tiles(cuda_device):
     assert (wi.cpu() - ref_i).abs().max().item() <= 1e-4
     assert (wz.cpu() - ref_z).abs().max().item() <= 1e-4
     gi, gz = cf.warp_frame_and_codes(di, dz, torch.zeros_like(df), "forward", skip_zero_flow=True)
+    assert torch.equal(gi, di) and torch.equal(gz, dz)
+
+
+@pytest.mark.parametrize("mode", ["forward", "backward"])
+def test_warp_quad_row_view_mixed_tiles(cuda_device, mode):
+    """Odd-width codes (130x173 of a 260x346 sensor) are staged through the quad-row tensor map (four source rows per
+    map row, four boxes per channel, residue-major rows in shared memory).  Smooth flow with a discontinuity: ring tiles
+    and direct-gather tiles in one launch, several streams (the global source-row index crosses stream boundaries), the
+    last rows/columns of the plane (boxes run past the row end and past the channel end), and the gated copy."""
+    B, C, H, W = 5, 128, 260, 346   # 540 codes CTAs: above the one-wave threshold of the odd-pitch path
+    img, codes, flow = synth.warp_inputs(B, H, W, seed=31, code_channels=C, flow_kind="smooth")
+    flow[1, :, 60:150, 200:300] += 33.0
+    ref_i, ref_z = ref_port.warp_frame_and_codes(torch.from_numpy(img), torch.from_numpy(codes), torch.from_numpy(flow), mode)
+    di, dz, df = dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(flow, cuda_device)
+    wi, wz = cf.warp_frame_and_codes(di, dz, df, mode)
+    assert last_kernel() == "warp_tma_kernel"
+    assert (wi.cpu() - ref_i).abs().max().item() <= 1e-4
+    assert (wz.cpu() - ref_z).abs().max().item() <= 1e-4
+    gi, gz = cf.warp_frame_and_codes(di, dz, torch.zeros_like(df), mode, skip_zero_flow=True)
     assert torch.equal(gi, di) and torch.equal(gz, dz)
 
 
