@@ -92,9 +92,9 @@ __device__ __forceinline__ void warp_image_block(const WarpJob &ji, const float 
     }
 }
 
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, int c0, int c1, uint64_t *bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1)
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
 __device__ __forceinline__ bool elect_lane() {
@@ -106,16 +106,18 @@ __device__ __forceinline__ bool elect_lane() {
 // QUAD: tensors without a 16-byte row pitch (W % 4 != 0, e.g. the 130x173 codes of a 260x346 sensor).  No tensor map
 // can describe their rows, but the whole buffer seen as a matrix of 4*W floats per row -- four source rows side by side,
 // pitch 16*W bytes -- can: a [48 x 6] box at column (g % 4)*W + x0, map row g/4 is source rows g, g+4, .., g+20 (g = the
-// global source-row index (b*C + c)*H + y).  Four boxes (g = g0 .. g0+3, g0 the row of the tile's first source row) per
-// channel bring its 24 source rows, which land residue-major: row g0 + k sits in shared row (k % 4)*6 + k/4.  But
+// global source-row index (b*C + c)*H + y).  Four boxes (g = g0 .. g0+3, g0 the row of the tile's first source row)
+// bring a channel's 24 source rows, which land residue-major: row g0 + k is row k/4 of box k % 4.  But
 //   * the box column must be a multiple of 4 floats (a start coordinate that is not 16-byte aligned raises "illegal
 //     instruction" on the B200 -- scripts/experiments/quad_probe.cu), so a box starts at ((g % 4)*W + x0) & ~3 and its
 //     data sits ((g % 4)*W + x0) % 4 floats further right: the usable box is 45 columns;
 //   * that shift depends on q = g0 % 4, hence on the channel through c*H % 4.  A stage therefore holds 8 channels of
 //     one residue class -- channel stride P = 1, 2 or 4 for H % 4 == 0, H even, H odd -- so that q is uniform per stage
 //     and the tap offsets are recomputed per stage (a few integer operations), not per channel.
-// Each warp's elected lane issues the four boxes of one channel (32 instructions per stage from one thread would
-// serialise behind its own gather work).
+// Channels P apart are P*H/4 map rows apart -- a whole number -- so the map gets a third dimension (groups of P
+// channels, stride 4*W*P*H bytes) and ONE [48 x 6 x 8] box per residue brings the stage's 8 channels: 4 instructions per
+// stage (a 2-D map with one box per channel and residue, 32 instructions per stage spread over the 8 warps, measured
+// the same: 64x260x346 399 against 405 us -- the instruction count is not the bound).
 template <bool QUAD>
 __global__ void __launch_bounds__(256, 3)
 warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_in_tiles, WarpJob jz, int tiles_x, int tiles,
@@ -202,7 +204,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
     }
     if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mxx; red[3][warp] = mxy; }
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], QUAD ? 8 : 1);
+        for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], 1);
         ptx::fence_barrier_init();
     }
     __syncthreads();
@@ -249,26 +251,28 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
         }
     }
 
+    constexpr int CSTR = QUAD ? (BH / 4) * BW : BH * BW;   // channel stride inside a stage
     const int nchunks = (c_end - c_begin + CC - 1) / CC;
     // QUAD: stage `chunk` holds channels first_channel(chunk) + P*i, i = 0..7 (the group's channel count is a multiple of
-    // 8*P); warp <-> channel i of the stage
+    // 8*P)
     const int P = QUAD ? ((H & 3) == 0 ? 1 : ((H & 1) ? 4 : 2)) : 1;
     auto first_channel = [&](int chunk) { return c_begin + (chunk % P) + P * CC * (chunk / P); };
     auto issue = [&](int chunk) {
         float *dst = stage0 + (chunk % STAGES) * STAGE_FLOATS;
         uint64_t *bar = &full[chunk % STAGES];
         if (QUAD) {
-            __syncwarp();
-            if (elect_lane()) {
-                ptx::mbar_expect_tx(bar, STAGE_BYTES / CC);
-                const int g0 = (b * jz.C + first_channel(chunk) + P * warp) * H + by;
+            if (warp == 0) {
+                __syncwarp();
+                if (elect_lane()) {
+                    ptx::mbar_expect_tx(bar, STAGE_BYTES);
+                    const int group = (b * jz.C + c_begin) / P + CC * (chunk / P);
+                    const int r0 = (chunk % P) * H + by;   // row inside the group of P channels
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int g = g0 + j;
-                    tma_load_2d(dst + (warp * BH + j * (BH / 4)) * BW, &tmap, ((g & 3) * W + bx) & ~3, g >> 2, bar);
+                    for (int j = 0; j < 4; ++j)
+                        tma_load_3d(dst + j * (CC * (BH / 4) * BW), &tmap, (((r0 + j) & 3) * W + bx) & ~3, (r0 + j) >> 2, group, bar);
                 }
+                __syncwarp();
             }
-            __syncwarp();
         } else if (tid == 0) {
             ptx::mbar_expect_tx(bar, STAGE_BYTES);
             ptx::tma_load_4d(dst, &tmap, bx, by, c_begin + chunk * CC, b, bar);
@@ -289,10 +293,10 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
             if (!live[j]) continue;
             float *o = out_b + (size_t)c0 * plane + (size_t)y * W + xl + 16 * j;
             int a0 = s00[j], a1 = s01[j], a2 = s10[j], a3 = s11[j];
-            if (QUAD) {  // row g0 + k -> shared row (k%4)*6 + k/4, shifted right by (((g0 + k) % 4)*W + x0) % 4
+            if (QUAD) {  // row g0 + k -> row k/4 of box k%4 ([8 channels][6 rows][48]), shifted right by (((g0 + k) % 4)*W + x0) % 4
                 const int k0 = s00[j], k1 = s10[j];
-                const int row0 = ((k0 & 3) * (BH / 4) + (k0 >> 2)) * BW + ((((k0 + q) & 3) * W + bx) & 3);
-                const int row1 = ((k1 & 3) * (BH / 4) + (k1 >> 2)) * BW + ((((k1 + q) & 3) * W + bx) & 3);
+                const int row0 = ((k0 & 3) * (CC * (BH / 4)) + (k0 >> 2)) * BW + ((((k0 + q) & 3) * W + bx) & 3);
+                const int row1 = ((k1 & 3) * (CC * (BH / 4)) + (k1 >> 2)) * BW + ((((k1 + q) & 3) * W + bx) & 3);
                 a0 = row0 + s01[j]; a1 = row0 + s11[j]; a2 = row1 + s01[j]; a3 = row1 + s11[j];
             }
             const float *s0 = st + a0, *s1 = st + a1, *s2 = st + a2, *s3 = st + a3;
@@ -300,10 +304,10 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
             float v[CC][4];  // all 32 tap loads before the first store (LDS/STG interleaving serialises on aliasing)
 #pragma unroll
             for (int c = 0; c < CC; ++c) {
-                v[c][0] = s0[c * (BH * BW)];
-                v[c][1] = s1[c * (BH * BW)];
-                v[c][2] = s2[c * (BH * BW)];
-                v[c][3] = s3[c * (BH * BW)];
+                v[c][0] = s0[c * CSTR];
+                v[c][1] = s1[c * CSTR];
+                v[c][2] = s2[c * CSTR];
+                v[c][3] = s3[c * CSTR];
             }
 #pragma unroll
             for (int c = 0; c < CC; ++c) {
@@ -338,10 +342,11 @@ int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r;
     if (quad) {
-        cuuint64_t dims[2] = {(cuuint64_t)jz.W * 4, (cuuint64_t)(src_rows / 4)};
-        cuuint64_t strides[1] = {(cuuint64_t)jz.W * 16};
-        cuuint32_t box[2] = {BW, BH / 4};
-        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(jz.img), dims, strides, box, estr,
+        const int P = (jz.H & 3) == 0 ? 1 : ((jz.H & 1) ? 4 : 2);   // as in the kernel
+        cuuint64_t dims[3] = {(cuuint64_t)jz.W * 4, (cuuint64_t)P * jz.H / 4, (cuuint64_t)(src_rows / ((int64_t)P * jz.H))};
+        cuuint64_t strides[2] = {(cuuint64_t)jz.W * 16, (cuuint64_t)jz.W * 4 * P * jz.H};
+        cuuint32_t box[3] = {BW, BH / 4, CC};
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(jz.img), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
