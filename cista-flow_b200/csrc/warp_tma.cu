@@ -173,13 +173,15 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
     bool live[2];
     int x0a[2], y0a[2];
     int mnx = INT_MAX, mny = INT_MAX, mxx = -1, mxy = -1;
-    // QUAD: the two half-warps sit 4 rows apart -- shared rows rr and rr + 4 are neighbours (16 banks apart), rr and
-    // rr + 1 are 6 rows = 0 banks apart
-    const int y = ty * TH + (QUAD ? (warp & 3) + 8 * (warp >> 2) + 4 * (lane >> 4) : 2 * warp + (lane >> 4));
-    const int xl = tx * TW + (lane & 15);
+    // QUAD: source rows one apart sit in different boxes, a multiple of 32 banks apart, and no pair of rows is 16 banks
+    // apart for every vertical flow gradient (half-warps 4 rows apart: 13.4 M bank conflicts at 32x260x346 against
+    // 8.6 M for the aligned kernel at 32x260x352) -- a warp pass is 32 px of ONE row there, pixel k on row 2*warp + k
+    const int xl = tx * TW + (QUAD ? lane : (lane & 15));
+    const int yl = ty * TH + 2 * warp + (QUAD ? 0 : (lane >> 4));
+    constexpr int KX = QUAD ? 0 : 16, KY = QUAD ? 1 : 0;   // pixel k of a thread: (xl + KX*k, yl + KY*k)
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        const int x = xl + 16 * k;
+        const int x = xl + KX * k, y = yl + KY * k;
         live[k] = x < W && y < H;
         if (live[k]) {
             if (identity) {
@@ -227,7 +229,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
 #pragma unroll
         for (int k = 0; k < 2; ++k)
             if (live[k]) {
-                const int p = y * W + xl + 16 * k;
+                const int p = (yl + KY * k) * W + xl + KX * k;
                 for (int c0 = c_begin; c0 < c_end; c0 += 8) warp_pixel<8>(img_b, out_b, taps[k], p, c0, c_end, plane);
             }
         return;
@@ -291,7 +293,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             if (!live[j]) continue;
-            float *o = out_b + (size_t)c0 * plane + (size_t)y * W + xl + 16 * j;
+            float *o = out_b + (size_t)c0 * plane + (size_t)(yl + KY * j) * W + xl + KX * j;
             int a0 = s00[j], a1 = s01[j], a2 = s10[j], a3 = s11[j];
             if (QUAD) {  // row g0 + k -> row k/4 of box k%4 ([8 channels][6 rows][48]), shifted right by (((g0 + k) % 4)*W + x0) % 4
                 const int k0 = s00[j], k1 = s10[j];
