@@ -337,7 +337,8 @@ int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const
     // one wave of CTAs or less is latency-bound and the four-box stages land later than the direct gather's taps
     // (1x260x346: 21.8 against 14.2 us)
     const int64_t quad_ctas = (int64_t)ceil_div(jz.W, TW) * ceil_div(jz.H, TH) * ceil_div(jz.C, CH_PER_CTA) * B;
-    if (quad && (jz.C % (4 * CC) != 0 || jz.W < 16 || (quad_ctas < 3 * (int64_t)sm_count() && !(env_quad && !strcmp(env_quad, "1"))) || src_rows > INT_MAX || (env_quad && !strcmp(env_quad, "0")))) return 1;
+    // (planes smaller than a box stay on the direct path too)
+    if (quad && (jz.C % (4 * CC) != 0 || jz.W < 16 || jz.H < BH || (quad_ctas < 3 * (int64_t)sm_count() && !(env_quad && !strcmp(env_quad, "1"))) || src_rows > INT_MAX || (env_quad && !strcmp(env_quad, "0")))) return 1;
     TensorMapEncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return 1;
     CUtensorMap tmap;
