@@ -259,3 +259,44 @@ print("OK", len(done))
 """ % ROOT
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.parametrize("H,W", [(130, 173), (33, 51), (312, 485), (35, 22), (36, 27)])
+def test_quad_row_view_index_math(H, W):
+    """The odd-pitch warp stages codes through a tensor map over the buffer seen as [groups of P channels][P*H/4 rows]
+    [4*W floats] (warp_tma.cu, QUAD).  This restates the index arithmetic of the issue side (four [48 x 6 x 8] boxes per
+    stage at 16-byte aligned columns) and of the consumer side (box k%4, row k/4, column shift) in NumPy and checks
+    that every (channel, source row, column) of a stage is found where the consumer looks for it."""
+    B, C, BW, BH, CC = 2, 64, 48, 24, 8
+    P = 1 if H % 4 == 0 else (4 if H % 2 else 2)
+    rng = np.random.default_rng(H * 1000 + W)
+    buf = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    view = buf.reshape(B * C // P, P * H // 4, 4 * W)          # the 3-D tensor map: dims (4W, P*H/4, B*C/P)
+
+    def box(col, row, grp):                                       # TMA tile load, zero fill outside the map
+        out = np.zeros((CC, BH // 4, BW), np.float32)
+        for ci in range(CC):
+            for ri in range(BH // 4):
+                for xi in range(BW):
+                    g, r, x = grp + ci, row + ri, col + xi
+                    if g < view.shape[0] and r < view.shape[1] and x < view.shape[2]:
+                        out[ci, ri, xi] = view[g, r, x]
+        return out
+
+    for b, c_begin, chunk, by, bx in [(0, 0, 0, 0, 0), (1, 0, 1, 5, 7), (1, 0, 3, H - 20, max(W - 45, 0)), (0, 0, 7, 17, 2)]:
+        pp = chunk % P
+        first_channel = c_begin + pp + P * CC * (chunk // P)
+        group = (b * C + c_begin) // P + CC * (chunk // P)
+        r0 = pp * H + by
+        stage = np.stack([box((((r0 + j) & 3) * W + bx) & ~3, (r0 + j) >> 2, group) for j in range(4)])   # [4][8][6][48]
+        flat = stage.reshape(-1)
+        q = ((b * C + first_channel) * H + by) & 3
+        assert q == r0 & 3
+        for k in range(min(BH, H - by)):
+            shift = (((k + q) & 3) * W + bx) & 3
+            row = ((k & 3) * (CC * (BH // 4)) + (k >> 2)) * BW + shift
+            for i in range(CC):
+                c = first_channel + P * i
+                n = min(BW - 3, W - bx)
+                got = flat[i * (BH // 4) * BW + row: i * (BH // 4) * BW + row + n]
+                assert np.array_equal(got, buf[b, c, by + k, bx:bx + n]), (b, c, k)
