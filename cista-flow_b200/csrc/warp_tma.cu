@@ -28,8 +28,9 @@
 //     28 % / 42 % against 44 % / 57 % for this kernel at 180x240 / 480x640 -- occupancy (3 small CTAs,
 //     2 pixels per thread) beats bytes saved.
 // The optional image part (1 channel, full resolution) of the per-frame step rides in the same
-// launch through the direct path.  Needs a 16-byte aligned row pitch (W % 4 == 0) for the tensor
-// map; other shapes use warp.cu.
+// launch through the direct path.  Row pitches that are not a multiple of 16 bytes (W % 4 != 0) go
+// through the quad-row tensor map (QUAD, below) when C % 32 == 0 and the grid is at least one full
+// wave; everything else uses warp.cu.
 #include <string.h>
 
 #include "tma.cuh"
