@@ -174,9 +174,10 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
     bool live[2];
     int x0a[2], y0a[2];
     int mnx = INT_MAX, mny = INT_MAX, mxx = -1, mxy = -1;
-    // QUAD: source rows one apart sit in different boxes, a multiple of 32 banks apart, and no pair of rows is 16 banks
-    // apart for every vertical flow gradient (half-warps 4 rows apart: 13.4 M bank conflicts at 32x260x346 against
-    // 8.6 M for the aligned kernel at 32x260x352) -- a warp pass is 32 px of ONE row there, pixel k on row 2*warp + k
+    // QUAD: a warp pass is 32 px of ONE row, pixel k on row 2*warp + k.  Output rows are only 4-byte aligned there: a
+    // 64-byte half-warp store touches 3 sectors, a 128-byte warp store 5 (ncu at 32x260x346: 17.1 M -> 14.7 M store
+    // sectors, 402 -> 384 us at 64 streams, although LDS wavefronts rose 25.4 M -> 28.5 M).  Source rows one apart sit
+    // in different boxes a multiple of 32 banks apart, so the 16 x 2 layout has no conflict-free row pairing anyway
     const int xl = tx * TW + (QUAD ? lane : (lane & 15));
     const int yl = ty * TH + 2 * warp + (QUAD ? 0 : (lane >> 4));
     constexpr int KX = QUAD ? 0 : 16, KY = QUAD ? 1 : 0;   // pixel k of a thread: (xl + KX*k, yl + KY*k)
