@@ -29,6 +29,7 @@ CASES = {
     "cfg3_260x346_b1": (260, 346, 1, 50000),
     "cfg3_260x346_b64": (260, 346, 64, 50000),
     "cfg5_480x640_b8": (480, 640, 8, 100000),
+    "cfg5_480x640_b64": (480, 640, 64, 100000),
     "cfg4_624x970_b1": (624, 970, 1, 1000000),
 }
 
