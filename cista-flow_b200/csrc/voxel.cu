@@ -386,7 +386,8 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
 }
 
 // One thread per run of equal keys (= one output pixel column).  The run is in
-// event order; bin indices are non-decreasing along it.  For each bin: first
+// event order; for time-sorted events bin indices are non-decreasing along it (runs that are not take
+// the order-agnostic walk at the top of the kernel).  For each bin: first
 // the left weights of the events with ti == bin, then the right weights of the
 // events with ti == bin-1 -- the order of the reference's two scatter-adds.
 __global__ void __launch_bounds__(256)
@@ -408,6 +409,56 @@ det_accumulate_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restr
     w.b = -1;
     locate_window(w, vals[i], off, ev, B);
     float *cell0 = out + ((int64_t)b * nb * planes + chan) * plane + pix;  // bin 0 of this column
+
+    // The fast walk below needs the run's bin indices to be non-decreasing (time-sorted events).  The reference's
+    // scatter-adds do not depend on that, so a run that breaks it (jittered / unsorted stamps, concatenated packs)
+    // takes the order-agnostic walk: per bin, the whole run in event order.
+    {
+        int64_t e = i;
+        int last_bin = -1;
+        bool monotone = true;
+        while (e < n && keys[e] == k) {
+            const Binned bb = bin_event(load_event(ev, vals[e]), w, nb, H, W, flavour);
+            monotone = monotone && bb.bin >= last_bin;
+            last_bin = bb.bin;
+            ++e;
+        }
+        if (!monotone) {
+            for (int bin = 0; bin < nb; ++bin) {
+                float acc = 0.f;
+                bool touched = false;
+                if (flavour == CF_FLAVOUR_MVSEC) {  // one index_put_ per bin: left and right weights interleave in event order
+                    for (int64_t j = i; j < e; ++j) {
+                        const Binned bb = bin_event(load_event(ev, vals[j]), w, nb, H, W, flavour);
+                        if (bb.bin != bin && bb.bin != bin - 1) continue;
+                        double wl, wr;
+                        weights_mvsec(bb, wl, wr);
+                        acc = __fadd_rn(acc, (float)(bb.bin == bin ? wl : wr));
+                        touched = true;
+                    }
+                } else {
+                    for (int pass = 0; pass < 2; ++pass) {  // all left weights (ti == bin), then all right ones (ti == bin-1)
+                        for (int64_t j = i; j < e; ++j) {
+                            const Binned bb = bin_event(load_event(ev, vals[j]), w, nb, H, W, flavour);
+                            if (bb.bin != bin - pass) continue;
+                            if (flavour == CF_FLAVOUR_TORCH) {
+                                float wl, wr;
+                                weights_f32(bb, wl, wr);
+                                acc = __fadd_rn(acc, pass ? wr : wl);
+                            } else {
+                                double wl, wr;
+                                weights_f64(bb, wl, wr);
+                                acc = (float)__dadd_rn((double)acc, pass ? wr : wl);
+                            }
+                            touched = true;
+                        }
+                    }
+                }
+                if (touched) cell0[(int64_t)bin * planes * plane] = acc;
+            }
+            return;
+        }
+    }
 
     int64_t pos = i, prev_s = i, prev_e = i;
     for (int bin = 0; bin < nb; ++bin) {

@@ -34,3 +34,26 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda", 0)
+
+
+class _ParityReport:
+    """Collects the agreement fractions the GPU parity tests measure (north_star: ">= 95 % tolerance-agreement")
+    and writes them to gpurun_out/parity_report.json at the end of the session."""
+
+    def __init__(self):
+        self.rows = []
+
+    def add(self, test, **kw):
+        self.rows.append({"test": test, **{k: (float(v) if isinstance(v, (float, np.floating)) else v) for k, v in kw.items()}})
+
+
+@pytest.fixture(scope="session")
+def parity_report():
+    rep = _ParityReport()
+    yield rep
+    if rep.rows:
+        import json
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.json"), "w") as fh:
+            json.dump(rep.rows, fh, indent=1)

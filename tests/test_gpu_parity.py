@@ -38,6 +38,14 @@ def assert_voxel_close(got, ref, mag=None):
     m = np.abs(ref.astype(np.float64)) if mag is None else np.maximum(mag.astype(np.float64), np.abs(ref.astype(np.float64)))
     tol = 1e-5 * (m + 1.0)
     assert (err <= tol).all(), f"max err {err.max():.3e}"
+    # ... and to the letter of north_star: the fraction of cells inside 1e-5 * (|ref| + 1) must be >= 95 %
+    frac = float((err <= 1e-5 * (np.abs(ref.astype(np.float64)) + 1.0)).mean()) if err.size else 1.0
+    assert frac >= 0.95, f"only {frac:.4f} of the cells within 1e-5*(|ref|+1)"
+    VOXEL_FRACTIONS.append(frac)
+    return frac
+
+
+VOXEL_FRACTIONS = []   # literal-tolerance agreement of every atomic-mode comparison of this session
 
 
 # ------------------------------------------------------------------ voxel ---
@@ -389,7 +397,7 @@ def test_warp_full_size_properties(cuda_device):
 
 @pytest.mark.parametrize("mode", ["forward", "backward"])
 @pytest.mark.parametrize("shape,flow_kind", [((2, 3, 18, 22), "noise"), ((1, 128, 90, 120), "smooth"), ((2, 5, 31, 45), "smooth")])
-def test_warp_backward_matches_autograd_of_the_reference_ops(cuda_device, mode, shape, flow_kind):
+def test_warp_backward_matches_autograd_of_the_reference_ops(cuda_device, parity_report, mode, shape, flow_kind):
     """gradients of forwardWarp / backWarp w.r.t. image (the bilinear splat) and flow against
     torch.autograd through the oracle port (F.grid_sample, reflection padding) on CPU."""
     B, C, H, W = shape
@@ -413,9 +421,11 @@ def test_warp_backward_matches_autograd_of_the_reference_ops(cuda_device, mode, 
     err = (df.grad.cpu() - rf.grad).abs()
     assert err.max().item() <= 2e-3 * scale_f, err.max().item()
     assert (err > 1e-4 * scale_f).float().mean().item() < 1e-3
+    parity_report.add("warp_backward_flow_gradient", mode=mode, shape=list(shape), flow_kind=flow_kind, elements=err.numel(),
+                      above_1e-4_scale=int((err > 1e-4 * scale_f).sum()), max_err_over_scale=err.max().item() / scale_f)
 
 
-def test_warp_backward_fused_half_resolution_flow(cuda_device):
+def test_warp_backward_fused_half_resolution_flow(cuda_device, parity_report):
     """Codes at half resolution warped with the full-resolution flow (e2v_model.py:190): the kernel also applies the
     adjoint of the x0.5 bilinear down-sampling.  Oracle: autograd through F.interpolate + grid_sample."""
     B, C, H, W = 2, 16, 36, 48
@@ -431,6 +441,8 @@ def test_warp_backward_fused_half_resolution_flow(cuda_device):
     err = (df.grad.cpu() - rf.grad).abs()
     scale = max(1.0, float(rf.grad.abs().max()))
     assert err.max().item() <= 2e-3 * scale and (err > 1e-4 * scale).float().mean().item() < 1e-3
+    parity_report.add("warp_backward_flow_gradient_half_res", elements=err.numel(), **{"above_1e-4_scale": int((err > 1e-4 * scale).sum())},
+                      max_err_over_scale=err.max().item() / scale)
 
 
 def test_warp_rejects_cpu_and_grad(cuda_device):
@@ -560,7 +572,18 @@ def test_fwl_golden_and_config_shape(golden, cuda_device):
 
 # ------------------------------------------------------------------- corr ---
 def corr_err(got, ref):
-    return float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() / max(np.abs(ref).max(), 1e-30))
+    """Normwise error max|err| / max|ref|, after asserting the element-wise agreement north_star asks for:
+    the fraction of elements with |err| <= 1e-3 * (|ref| + rms(ref)) must be >= 95 %."""
+    g, r = got.astype(np.float64), ref.astype(np.float64)
+    err = np.abs(g - r)
+    rms = float(np.sqrt(np.mean(r * r))) if r.size else 0.0
+    frac = float((err <= 1e-3 * (np.abs(r) + rms)).mean()) if err.size else 1.0
+    CORR_FRACTIONS.append(frac)
+    assert frac >= 0.95, f"only {frac:.4f} of the elements within 1e-3*(|ref|+rms)"
+    return float(err.max() / max(np.abs(r).max(), 1e-30))
+
+
+CORR_FRACTIONS = []   # H3 agreement fraction of every correlation / lookup comparison of this session
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
@@ -743,3 +766,19 @@ def test_model_trace_replay(golden, cuda_device, trace):
                                      dev_t(g["flow_final"], cuda_device), "forward")
     np.testing.assert_allclose(wi.cpu().numpy(), g["warp0/out"], rtol=0, atol=1e-4)
     np.testing.assert_allclose(wz.cpu().numpy(), g["warp1/out"], rtol=0, atol=1e-4)
+
+
+# ------------------------------------------------- agreement summaries (run last) ---
+def test_zz_voxel_atomic_agreement_summary(parity_report):
+    """Runs last in this file's voxel block order-independently: reports min / mean of the literal-tolerance fractions."""
+    if VOXEL_FRACTIONS:
+        parity_report.add("voxel_atomic_literal_1e-5*(|ref|+1)", comparisons=len(VOXEL_FRACTIONS),
+                          min_fraction=min(VOXEL_FRACTIONS), mean_fraction=float(np.mean(VOXEL_FRACTIONS)))
+        print(f"voxel atomic mode: {len(VOXEL_FRACTIONS)} comparisons, min fraction within 1e-5*(|ref|+1) = {min(VOXEL_FRACTIONS):.6f}")
+
+
+def test_zz_corr_agreement_summary(parity_report):
+    if CORR_FRACTIONS:
+        parity_report.add("corr_H3_1e-3*(|ref|+rms)", comparisons=len(CORR_FRACTIONS), min_fraction=min(CORR_FRACTIONS),
+                          mean_fraction=float(np.mean(CORR_FRACTIONS)))
+        print(f"correlation: {len(CORR_FRACTIONS)} comparisons, min fraction within 1e-3*(|ref|+rms) = {min(CORR_FRACTIONS):.6f}")

@@ -1,0 +1,121 @@
+"""Round-2 parity cases (GPU only): oracle comparisons at the FULL BASELINE sizes (not only properties),
+the order-agnostic deterministic walk, and the pieces added this round (fused upflow8 + unpad + warp,
+device-side windowing by N events).  Tolerances as in tests/test_gpu_parity.py (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import cistaflow_b200 as cf
+from cistaflow_b200 import synth
+from oracle import explicit, ref_port
+
+from test_gpu_parity import assert_voxel_close, bits, dev_t
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------ voxel ---
+@pytest.mark.parametrize("flavour", ["torch", "numpy"])
+def test_voxel_deterministic_unsorted_timestamps(cuda_device, flavour):
+    """The reference's scatter-adds do not depend on the stamps being sorted; the deterministic mode must not either
+    (round-1 ADVICE: the per-pixel walk assumed non-decreasing bins and silently dropped events).  Stamps are
+    shuffled inside each window, first/last rows kept (they define t0 and dT), so every t* stays in [0, nb-1]."""
+    h, w, n, batch = 48, 64, 6000, 3
+    ev, off = synth.event_windows(batch, n, h, w, seed=123)
+    rng = np.random.default_rng(5)
+    for b in range(batch):
+        s, e = off[b] + 1, off[b + 1] - 1
+        ev[s:e, 0] = ev[s:e, 0][rng.permutation(e - s)]
+    fl = explicit.FLAVOUR_TORCH if flavour == "torch" else explicit.FLAVOUR_NUMPY
+    ref = np.stack([explicit.voxel_grid_sequential(ev[off[b]:off[b + 1]], 5, w, h, fl) for b in range(batch)])
+    ev_d, off_d = dev_t(ev, cuda_device), dev_t(off, cuda_device)
+    det = cf.events_to_voxel_grid_batched(ev_d, off_d, 5, w, h, flavour=flavour, mode="deterministic").cpu().numpy()
+    assert np.array_equal(bits(det), bits(ref))
+    pos = ev.copy()
+    pos[:, 3] = 1.0
+    mag = np.stack([explicit.voxel_grid_sequential(pos[off[b]:off[b + 1]], 5, w, h, fl) for b in range(batch)])
+    atom = cf.events_to_voxel_grid_batched(ev_d, off_d, 5, w, h, flavour=flavour, mode="atomic").cpu().numpy()
+    assert_voxel_close(atom, ref, mag)
+
+
+def test_voxel_mvsec_deterministic_unsorted_timestamps(cuda_device):
+    """Same for the second voxeliser (one index_put_ per bin: left and right weights interleave in event order)."""
+    h, w, n = 40, 56, 5000
+    ev = synth.events(n, h, w, seed=321)
+    rng = np.random.default_rng(6)
+    ev[1:-1, 0] = ev[1:-1, 0][rng.permutation(n - 2)]
+    ev[:, 3] = np.where(ev[:, 3] == 0, -1.0, 1.0)
+    xytp = ev[:, [1, 2, 0, 3]]
+    ref = ref_port.mvsec_voxel_torch(torch.from_numpy(xytp[:, 0]), torch.from_numpy(xytp[:, 1]), torch.from_numpy(xytp[:, 2]),
+                                     torch.from_numpy(xytp[:, 3]), 5, h, w).numpy()
+    off = torch.tensor([0, n], dtype=torch.int64, device=cuda_device)
+    got = cf.events_to_voxel_grid_batched(dev_t(ev, cuda_device), off, 5, w, h, flavour="mvsec", mode="deterministic")[0]
+    assert np.array_equal(bits(got.cpu().numpy()), bits(ref))
+
+
+def test_voxel_full_size_vs_sequential_oracle(cuda_device, parity_report):
+    """configs[3] at full size: 1 M events at 624x970 against the plain-C sequential oracle -- deterministic mode
+    bit-exact (both flavours), atomic mode within tolerance, fused normalisation against the explicit oracle."""
+    n, h, w = 1_000_000, 624, 970
+    ev = synth.events(n, h, w, seed=synth.seed_for(3))
+    ev_d = dev_t(ev, cuda_device)
+    off = torch.tensor([0, n], dtype=torch.int64, device=cuda_device)
+    pos = ev.copy()
+    pos[:, 3] = 1.0
+    for flavour, fl in (("torch", explicit.FLAVOUR_TORCH), ("numpy", explicit.FLAVOUR_NUMPY)):
+        ref = explicit.voxel_grid_sequential(ev, 5, w, h, fl)
+        mag = explicit.voxel_grid_sequential(pos, 5, w, h, fl)
+        det = cf.events_to_voxel_grid_batched(ev_d, off, 5, w, h, flavour=flavour, mode="deterministic")[0].cpu().numpy()
+        assert np.array_equal(bits(det), bits(ref)), flavour
+        atom = cf.events_to_voxel_grid_batched(ev_d, off, 5, w, h, flavour=flavour, mode="atomic")[0].cpu().numpy()
+        frac = assert_voxel_close(atom, ref, mag)
+        parity_report.add("voxel_full_size_624x970_1M", flavour=flavour, deterministic_bit_exact=True,
+                          atomic_fraction_within_literal_tol=frac, atomic_max_abs_err=float(np.abs(atom - ref).max()))
+    thr = 25.0 / 5
+    fused = cf.events_to_voxel_grid_batched(ev_d, off, 5, w, h, normalize="std", filter_hot_pixel=True, flavour="numpy",
+                                            mode="atomic")[0].cpu().numpy()
+    np.testing.assert_allclose(fused, explicit.preprocess(ref, "std", thr), rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------- warp ---
+@pytest.mark.parametrize("h,w", [(480, 640), (624, 970)])
+@pytest.mark.parametrize("flow_kind", ["smooth", "noise"])
+def test_warp_codes_full_size_vs_oracle(cuda_device, parity_report, h, w, flow_kind):
+    """configs[3]/[4] at full size with the model's 128 code channels: frame [1,1,H,W] + codes [1,128,H/2,W/2]
+    against the reference's grid_sample path (oracle port) -- |err| <= 1e-4 on every element."""
+    img, codes, flow = synth.warp_inputs(1, h, w, seed=17, code_channels=128, flow_kind=flow_kind)
+    ri, rz = ref_port.warp_frame_and_codes(torch.from_numpy(img), torch.from_numpy(codes), torch.from_numpy(flow), "forward")
+    wi, wz = cf.warp_frame_and_codes(dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(flow, cuda_device), "forward")
+    ei, ez = (wi.cpu() - ri).abs(), (wz.cpu() - rz).abs()
+    parity_report.add("warp_full_size", H=h, W=w, flow_kind=flow_kind, max_err_frame=ei.max().item(), max_err_codes=ez.max().item(),
+                      fraction_within_1e-4=float(((ez <= 1e-4).float().mean() + (ei <= 1e-4).float().mean()) / 2))
+    assert ei.max().item() <= 1e-4 and ez.max().item() <= 1e-4
+    bi, bz = ref_port.warp_frame_and_codes(torch.from_numpy(img), torch.from_numpy(codes), torch.from_numpy(flow), "backward")
+    vi, vz = cf.warp_frame_and_codes(dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(flow, cuda_device), "backward")
+    assert (vi.cpu() - bi).abs().max().item() <= 1e-4 and (vz.cpu() - bz).abs().max().item() <= 1e-4
+
+
+# ------------------------------------------------------- batched, 64 streams ---
+def test_voxel_64_streams_480x640_vs_oracle(cuda_device, parity_report):
+    """The bench's own voxel launch (64 windows of 100 000 events at 480x640, fused std normalisation, hot-pixel
+    filter): 4 distinct windows tiled to 64 like bench.py; every window against the sequential oracle + preprocess."""
+    h, w, n, B = 480, 640, 100000, 64
+    ev4, off4 = synth.event_windows(4, n, h, w, seed=4321)
+    ev = np.concatenate([ev4] * (B // 4))
+    off = np.arange(B + 1, dtype=np.int64) * n
+    raw = cf.events_to_voxel_grid_batched(dev_t(ev, cuda_device), dev_t(off, cuda_device), 5, w, h, flavour="numpy",
+                                          mode="atomic").cpu().numpy()
+    fused = cf.events_to_voxel_grid_batched(dev_t(ev, cuda_device), dev_t(off, cuda_device), 5, w, h, normalize="std",
+                                            filter_hot_pixel=True, flavour="numpy", mode="atomic").cpu().numpy()
+    fr = []
+    for b in range(4):
+        win = ev4[off4[b]:off4[b + 1]]
+        ref = explicit.voxel_grid_sequential(win, 5, w, h, explicit.FLAVOUR_NUMPY)
+        pos = win.copy()
+        pos[:, 3] = 1.0
+        mag = explicit.voxel_grid_sequential(pos, 5, w, h, explicit.FLAVOUR_NUMPY)
+        ref_n = explicit.preprocess(ref, "std", 5.0)
+        for k in range(b, B, 4):
+            fr.append(assert_voxel_close(raw[k], ref, mag))
+            np.testing.assert_allclose(fused[k], ref_n, rtol=1e-4, atol=1e-4)
+    parity_report.add("voxel_64x480x640_bench_launch", windows=B, min_fraction_within_literal_tol=min(fr))
