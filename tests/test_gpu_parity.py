@@ -422,7 +422,7 @@ def test_warp_backward_matches_autograd_of_the_reference_ops(cuda_device, parity
     assert err.max().item() <= 2e-3 * scale_f, err.max().item()
     assert (err > 1e-4 * scale_f).float().mean().item() < 1e-3
     parity_report.add("warp_backward_flow_gradient", mode=mode, shape=list(shape), flow_kind=flow_kind, elements=err.numel(),
-                      above_1e-4_scale=int((err > 1e-4 * scale_f).sum()), max_err_over_scale=err.max().item() / scale_f)
+                      above_1e4th_of_scale=int((err > 1e-4 * scale_f).sum()), max_err_over_scale=err.max().item() / scale_f)
 
 
 def test_warp_backward_fused_half_resolution_flow(cuda_device, parity_report):
@@ -441,7 +441,7 @@ def test_warp_backward_fused_half_resolution_flow(cuda_device, parity_report):
     err = (df.grad.cpu() - rf.grad).abs()
     scale = max(1.0, float(rf.grad.abs().max()))
     assert err.max().item() <= 2e-3 * scale and (err > 1e-4 * scale).float().mean().item() < 1e-3
-    parity_report.add("warp_backward_flow_gradient_half_res", elements=err.numel(), **{"above_1e-4_scale": int((err > 1e-4 * scale).sum())},
+    parity_report.add("warp_backward_flow_gradient_half_res", elements=err.numel(), above_1e4th_of_scale=int((err > 1e-4 * scale).sum()),
                       max_err_over_scale=err.max().item() / scale)
 
 

@@ -88,7 +88,7 @@ def test_warp_codes_full_size_vs_oracle(cuda_device, parity_report, h, w, flow_k
     wi, wz = cf.warp_frame_and_codes(dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(flow, cuda_device), "forward")
     ei, ez = (wi.cpu() - ri).abs(), (wz.cpu() - rz).abs()
     parity_report.add("warp_full_size", H=h, W=w, flow_kind=flow_kind, max_err_frame=ei.max().item(), max_err_codes=ez.max().item(),
-                      fraction_within_1e-4=float(((ez <= 1e-4).float().mean() + (ei <= 1e-4).float().mean()) / 2))
+                      fraction_within_tol=float(((ez <= 1e-4).float().mean() + (ei <= 1e-4).float().mean()) / 2))
     assert ei.max().item() <= 1e-4 and ez.max().item() <= 1e-4
     bi, bz = ref_port.warp_frame_and_codes(torch.from_numpy(img), torch.from_numpy(codes), torch.from_numpy(flow), "backward")
     vi, vz = cf.warp_frame_and_codes(dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(flow, cuda_device), "backward")
