@@ -24,6 +24,9 @@ trace_eiflow.npz / trace_eraft.npz
             hot-path calls recorded inside DCEIFlowCistaNet / ERAFTCistaNet
             (seeded random-init weights, base_channels=16 to keep the files
             small) on the 3rd recurrent frame of a synthetic 128x160 stream.
+trace3_eiflow.npz / trace3_eraft.npz
+            three CONSECUTIVE recurrent frames (4th-6th) of the default-size models
+            (180x240, base_channels 64): hot-path inputs + reference outputs per frame.
 """
 import argparse
 import os
@@ -305,6 +308,95 @@ def make_trace(model_mode: str, fname: str):
     save(fname, **out)
 
 
+def make_trace_multi(model_mode: str, fname: str, first: int = 3, frames: int = 3):
+    """Consecutive recurrent frames `first .. first+frames-1` (the drivers skip the first 3 too) of the reference model
+    at its DEFAULT size (180x240, base_channels 64): the hot-path INPUTS of every frame -- events, the feature maps the
+    encoder produced (first 32 of 256 channels: the contraction is linear in channels and D = 32 is a valid CorrBlock
+    call), every lookup's coords, the previous reconstruction, the final flow, the first 8 of 128 code channels -- and
+    the reference's own OUTPUTS for the last lookup (recomputed by the reference CorrBlock on the stored channel
+    subset; every 4th output channel kept), the warped frame and the warped code channels.  Events are stored as
+    (t f64, x u16, y u16, p u8); the voxel grid is checked against the oracle (pinned bit-exact by voxel.npz).  The GPU tests replay frame by frame."""
+    _stub_optional_imports()
+    from utils.configs import set_configs
+    from utils import event_process as ep
+    import e2v.e2v_model as em
+    import utils.flow_utils as fu
+
+    H, W, NEV, DSUB, CSUB = 180, 240, 15000, 32, 8
+    parser = argparse.ArgumentParser()
+    set_configs(parser)
+    cfgs = parser.parse_args(["--image_dim", str(H), str(W), "--model_mode", model_mode])
+    torch.manual_seed(0)
+    if model_mode == "cista-eiflow":
+        model = em.DCEIFlowCistaNet(cfgs)
+        import DCEIFlow.DCEIFlow as host
+    else:
+        model = em.ERAFTCistaNet(cfgs)
+        import ERAFT.eraft as host
+    model.eval()
+    rec = {"frame": -1, "n_lookup": 0, "n_warp": 0}
+    out = {}
+    RefCorr = host.CorrBlock
+
+    class TapCorr(RefCorr):
+        def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+            super().__init__(fmap1, fmap2, num_levels=num_levels, radius=radius)
+            if rec["frame"] >= 0:
+                f = rec["frame"]
+                out[f"f{f}/fmap1"], out[f"f{f}/fmap2"] = fmap1[:, :DSUB].numpy().copy(), fmap2[:, :DSUB].numpy().copy()
+                self.sub = RefCorr(fmap1[:, :DSUB].contiguous(), fmap2[:, :DSUB].contiguous(), num_levels=num_levels, radius=radius)
+
+        def __call__(self, coords):
+            res = super().__call__(coords)
+            if rec["frame"] >= 0:
+                f, k = rec["frame"], rec["n_lookup"]
+                out[f"f{f}/coords{k}"] = coords.numpy().copy()
+                out[f"f{f}/lookup_last"] = self.sub(coords)[:, ::4].numpy().copy()   # overwritten until the last call
+                rec["n_lookup"] += 1
+            return res
+
+    host.CorrBlock = TapCorr
+    ref_warp_frame = fu.FrameWarp.warp_frame
+
+    def tap_warp(self, I, flow):
+        res = ref_warp_frame(self, I, flow)
+        if rec["frame"] >= 0:
+            f, k = rec["frame"], rec["n_warp"]
+            sub = slice(0, CSUB) if I.shape[1] > CSUB else slice(None)
+            out[f"f{f}/warp{k}_in"], out[f"f{f}/warp{k}_out"] = I[:, sub].numpy().copy(), res[:, sub].numpy().copy()
+            rec["n_warp"] += 1
+        return res
+
+    fu.FrameWarp.warp_frame = tap_warp
+    try:
+        states, prev, vox_old = None, torch.zeros(1, 1, H, W), torch.zeros(1, 5, H, W)
+        with torch.no_grad():
+            for frame in range(first + frames):
+                ev = synth.events(NEV, H, W, synth.seed_for(1, frame))
+                f = frame - first
+                rec["frame"], rec["n_lookup"], rec["n_warp"] = (f if f >= 0 else -1), 0, 0
+                grid = ep.events_to_voxel_grid(ev.copy(), 5, W, H)
+                vox = np.asarray(ep.event_preprocess(grid.copy(), "std", True), np.float32)
+                if f >= 0:
+                    out[f"f{f}/ev_t"], out[f"f{f}/ev_x"] = ev[:, 0].copy(), ev[:, 1].astype(np.uint16)
+                    out[f"f{f}/ev_y"], out[f"f{f}/ev_p"] = ev[:, 2].astype(np.uint16), ev[:, 3].astype(np.uint8)
+                vox_t = torch.from_numpy(vox)[None]
+                if model_mode == "cista-eiflow":
+                    batch = {"event_voxel": vox_t, "rec_img0": prev}
+                else:
+                    batch = {"event_voxel": vox_t, "event_voxel_old": vox_old, "rec_img0": prev}
+                pred, flow_out, states = model(batch, states)
+                if f >= 0:
+                    out[f"f{f}/flow_final"] = flow_out["flow_final"].numpy().copy()
+                    out[f"f{f}/counts"] = np.array([rec["n_lookup"], rec["n_warp"]])
+                prev, vox_old = pred.clone(), vox_t
+    finally:
+        host.CorrBlock = RefCorr
+        fu.FrameWarp.warp_frame = ref_warp_frame
+    out["meta"] = np.array([H, W, NEV, frames, DSUB, CSUB])
+    save(fname, **out)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), f"reference checkout not found at {REF}"
     only = sys.argv[1:]
@@ -321,3 +413,6 @@ if __name__ == "__main__":
     if not only or "trace" in only:
         make_trace("cista-eiflow", "trace_eiflow.npz")
         make_trace("cista-eraft", "trace_eraft.npz")
+    if not only or "trace3" in only:
+        make_trace_multi("cista-eiflow", "trace3_eiflow.npz")
+        make_trace_multi("cista-eraft", "trace3_eraft.npz")

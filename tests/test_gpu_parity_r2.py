@@ -119,3 +119,44 @@ def test_voxel_64_streams_480x640_vs_oracle(cuda_device, parity_report):
             fr.append(assert_voxel_close(raw[k], ref, mag))
             np.testing.assert_allclose(fused[k], ref_n, rtol=1e-4, atol=1e-4)
     parity_report.add("voxel_64x480x640_bench_launch", windows=B, min_fraction_within_literal_tol=min(fr))
+
+
+# ------------------------------------------------ multi-frame model traces ---
+@pytest.mark.parametrize("trace", ["trace3_eiflow", "trace3_eraft"])
+def test_multi_frame_trace_replay(golden, cuda_device, parity_report, trace):
+    """Three CONSECUTIVE recurrent frames (4th-6th) of the default-size reference models (180x240, base_channels 64,
+    tests/golden/make_golden.py make_trace_multi): every frame's hot-path calls replayed through the CUDA path on the
+    tensors the reference model actually produced, against the reference's own outputs."""
+    from test_oracle_golden import trace3_events
+    from test_gpu_parity import corr_err
+    g = golden(trace)
+    H, W, nev, frames, dsub, csub = (int(v) for v in g["meta"])
+    frame_warp = cf.FrameWarp("forward")
+    worst = {"lookup": 0.0, "warp": 0.0, "voxel": 0.0}
+    for f in range(frames):
+        n_lookup, n_warp = (int(v) for v in g[f"f{f}/counts"])
+        ev = trace3_events(g, f)
+        ref_grid = explicit.voxel_grid_sequential(ev, 5, W, H, explicit.FLAVOUR_NUMPY)
+        grid = cf.events_to_voxel_grid(ev, 5, W, H, mode="deterministic")
+        assert np.array_equal(bits(grid), bits(ref_grid))
+        ref_norm = ref_port.preprocess_numpy(ref_grid, "std", True)
+        fused = cf.events_to_voxel_grid_batched(dev_t(ev, cuda_device), torch.tensor([0, len(ev)], device=cuda_device), 5, W, H,
+                                                normalize="std", filter_hot_pixel=True, flavour="numpy", mode="atomic")[0]
+        worst["voxel"] = max(worst["voxel"], float(np.abs(fused.cpu().numpy() - ref_norm).max()))
+        np.testing.assert_allclose(fused.cpu().numpy(), ref_norm, rtol=1e-4, atol=1e-4)
+        blk = cf.CorrBlock(dev_t(g[f"f{f}/fmap1"], cuda_device), dev_t(g[f"f{f}/fmap2"], cuda_device), num_levels=4, radius=4)
+        for k in range(n_lookup):
+            out = blk(dev_t(g[f"f{f}/coords{k}"], cuda_device))
+        e = corr_err(out[:, ::4].cpu().numpy(), g[f"f{f}/lookup_last"])
+        worst["lookup"] = max(worst["lookup"], e)
+        assert e <= 1e-3
+        flow = dev_t(g[f"f{f}/flow_final"], cuda_device)
+        wi, wz = cf.warp_frame_and_codes(dev_t(g[f"f{f}/warp0_in"], cuda_device), dev_t(g[f"f{f}/warp1_in"], cuda_device), flow, "forward")
+        ei = float(np.abs(wi.cpu().numpy() - g[f"f{f}/warp0_out"]).max())
+        ez = float(np.abs(wz.cpu().numpy() - g[f"f{f}/warp1_out"]).max())
+        worst["warp"] = max(worst["warp"], ei, ez)
+        assert ei <= 1e-4 and ez <= 1e-4
+        sep = frame_warp.warp_frame(dev_t(g[f"f{f}/warp0_in"], cuda_device), flow)
+        np.testing.assert_allclose(sep.cpu().numpy(), g[f"f{f}/warp0_out"], rtol=0, atol=1e-4)
+    parity_report.add("multi_frame_trace_replay", trace=trace, frames=frames, max_lookup_err_over_max=worst["lookup"],
+                      max_warp_abs_err=worst["warp"], max_fused_voxel_abs_err=worst["voxel"])

@@ -183,3 +183,33 @@ def test_fwl_ref_port_bit_exact(golden):
     var0, _, _ = ref_port.voxel_flow_warp(voxel, torch.zeros_like(disp))
     assert np.float32(var0.item()) == g["loss_zero_flow"]
 
+
+
+def trace3_events(g, f):
+    return np.stack([g[f"f{f}/ev_t"], g[f"f{f}/ev_x"].astype(np.float64), g[f"f{f}/ev_y"].astype(np.float64),
+                     g[f"f{f}/ev_p"].astype(np.float64)], axis=1)
+
+
+@pytest.mark.parametrize("trace", ["trace3_eiflow", "trace3_eraft"])
+def test_multi_frame_trace_through_oracle(golden, trace):
+    """Three consecutive recurrent frames of the default-size reference models (tests/golden/make_golden.py
+    make_trace_multi): the oracle port reproduces the stored reference outputs (warps bit for bit, lookups to sgemm blocking order)."""
+    g = golden(trace)
+    H, W, nev, frames, dsub, csub = (int(v) for v in g["meta"])
+    for f in range(frames):
+        n_lookup, n_warp = (int(v) for v in g[f"f{f}/counts"])
+        assert n_lookup in (6, 12) and n_warp == 2
+        pyr = ref_port.corr_pyramid(torch.from_numpy(g[f"f{f}/fmap1"]), torch.from_numpy(g[f"f{f}/fmap2"]), 4)
+        out = ref_port.corr_lookup(pyr, torch.from_numpy(g[f"f{f}/coords{n_lookup - 1}"]), 4)
+        # (the stored lookups came from a CorrBlock built inside the running model: same calls, but the sgemm blocking of
+        #  a D = 32 product differs between the two contexts -- 1e-7 relative, not bit-exact)
+        ref = g[f"f{f}/lookup_last"]
+        assert np.abs(out[:, ::4].numpy() - ref).max() <= 1e-6 * np.abs(ref).max()
+        flow = torch.from_numpy(g[f"f{f}/flow_final"])
+        wi, wz = ref_port.warp_frame_and_codes(torch.from_numpy(g[f"f{f}/warp0_in"]), torch.from_numpy(g[f"f{f}/warp1_in"]),
+                                               flow, "forward")
+        assert np.array_equal(wi.numpy(), g[f"f{f}/warp0_out"]) and np.array_equal(wz.numpy(), g[f"f{f}/warp1_out"])
+        ev = trace3_events(g, f)
+        assert ev.shape == (nev, 4) and np.all(np.diff(ev[:, 0]) >= 0)
+    # the recurrence is live: consecutive frames warp different states with different flows
+    assert not np.array_equal(g["f0/warp1_in"], g["f1/warp1_in"]) and not np.array_equal(g["f0/flow_final"], g["f1/flow_final"])
