@@ -43,6 +43,7 @@ SYMBOLS = {
     "cf_warp_frame_and_codes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "cf_flow_any": (_i, [_vp, _i64, _vp, _vp]),
     "cf_warp_frame_and_codes_gated": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    "cf_warp_frame_and_codes_upflow8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "cf_warp_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "cf_voxel_flow_warp_workspace_bytes": (_sz, [_i, _i, _i]),
     "cf_voxel_flow_warp": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -23,11 +23,11 @@ namespace cf {
 
 // implemented in warp_tma.cu: CF_OK / error, or 1 when the TMA-staged path does not apply
 int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const float *flow, int fH, int fW, float sign,
-                    int B, const int *gate, cudaStream_t stream);
+                    int B, const int *gate, const FlowLR &lr, cudaStream_t stream);
 
 static int launch_staged(const WarpJob &ji, bool with_image, const WarpJob &jz, const float *flow, int fH, int fW,
-                         float sign, int B, const int *gate, cudaStream_t stream) {
-    return launch_warp_tma(ji, with_image, jz, flow, fH, fW, sign, B, gate, stream);
+                         float sign, int B, const int *gate, const FlowLR &lr, cudaStream_t stream) {
+    return launch_warp_tma(ji, with_image, jz, flow, fH, fW, sign, B, gate, lr, stream);
 }
 
 // flag[0] = 1 iff any element of flow is non-zero (NaN counts, -0.0 does not: torch.Tensor.any()).  flag is zeroed
@@ -47,22 +47,23 @@ __global__ void __launch_bounds__(256) flow_any_kernel(const float *__restrict__
 template <int CPT>
 __global__ void __launch_bounds__(256, 4) warp_gather_kernel(WarpJob j, const float *__restrict__ flow,
                                                           int fH, int fW, float sign) {
-    run_job<CPT>(j, flow, fH, fW, sign, blockIdx.x, blockIdx.y, blockIdx.z, nullptr);
+    run_job<CPT>(j, flow, fH, fW, sign, blockIdx.x, blockIdx.y, blockIdx.z, nullptr, FlowLR{});
 }
 
 // image (CPT=1 per thread, few channels) + codes (CPT=8, 32 channels per thread) in one launch:
 // blockIdx.x < img.blocks_x*img.groups -> image part, the rest -> codes part.
 __global__ void __launch_bounds__(256, 4) warp_frame_and_codes_kernel(WarpJob ji, WarpJob jz,
                                                                    const float *__restrict__ flow,
-                                                                   int fH, int fW, float sign, const int *__restrict__ gate) {
+                                                                   int fH, int fW, float sign, const int *__restrict__ gate,
+                                                                   FlowLR lr) {
     const int b = blockIdx.y;
     int blk = blockIdx.x;
     const int n_img = ji.blocks_x * ji.groups;
     if (blk < n_img) {
-        run_job<1>(ji, flow, fH, fW, sign, blk % ji.blocks_x, blk / ji.blocks_x, b, gate);
+        run_job<1>(ji, flow, fH, fW, sign, blk % ji.blocks_x, blk / ji.blocks_x, b, gate, lr, true);
     } else {
         blk -= n_img;
-        run_job<8>(jz, flow, fH, fW, sign, blk % jz.blocks_x, blk / jz.blocks_x, b, gate);
+        run_job<8>(jz, flow, fH, fW, sign, blk % jz.blocks_x, blk / jz.blocks_x, b, gate, lr);
     }
 }
 
@@ -104,7 +105,7 @@ extern "C" int cf_warp(const float *img, const float *flow, float *out, int B, i
     if (int rc = make_job(j, img, out, C, H, W, flowH, flowW, cpt)) return rc;
     CF_REQUIRE(j.groups <= 65535, CF_ERR_INVALID_ARG, "cf_warp: too many channels");
     if (C >= 8) {  // multi-channel tensors: TMA-staged kernel when the shape allows it
-        const int rc = launch_staged(j, false, j, flow, flowH, flowW, sign, B, nullptr, stream);
+        const int rc = launch_staged(j, false, j, flow, flowH, flowW, sign, B, nullptr, FlowLR{}, stream);
         if (rc != 1) return rc;
     }
     dim3 grid(j.blocks_x, j.groups, B);
@@ -138,6 +139,24 @@ extern "C" int cf_warp_frame_and_codes(const float *img, const float *codes, con
     return cf_warp_frame_and_codes_gated(img, codes, flow, img_out, codes_out, B, Ci, Cz, H, W, sign, nullptr, stream_);
 }
 
+namespace cf {
+static int warp_frame_and_codes_impl(const float *img, const float *codes, const float *flow, float *img_out, float *codes_out,
+                                     int B, int Ci, int Cz, int H, int W, float sign, const int *gate, const FlowLR &lr,
+                                     cudaStream_t stream) {
+    WarpJob ji, jz;
+    if (int rc = make_job(ji, img, img_out, Ci, H, W, H, W, 1)) return rc;
+    if (int rc = make_job(jz, codes, codes_out, Cz, H / 2, W / 2, H, W, 8)) return rc;
+    {
+        const int rc = launch_staged(ji, true, jz, flow, H, W, sign, B, gate, lr, stream);
+        if (rc != 1) return rc;
+    }
+    dim3 grid(ji.blocks_x * ji.groups + jz.blocks_x * jz.groups, B);
+    warp_frame_and_codes_kernel<<<grid, 256, 0, stream>>>(ji, jz, flow, H, W, sign, gate, lr);
+    CF_LAUNCH_CHECK("warp_frame_and_codes_kernel");
+    return CF_OK;
+}
+}  // namespace cf
+
 extern "C" int cf_warp_frame_and_codes_gated(const float *img, const float *codes, const float *flow,
                                              float *img_out, float *codes_out, int B, int Ci, int Cz,
                                              int H, int W, float sign, const int *gate, cf_stream_t stream_) {
@@ -149,16 +168,31 @@ extern "C" int cf_warp_frame_and_codes_gated(const float *img, const float *code
     CF_REQUIRE(sign == 1.f || sign == -1.f, CF_ERR_INVALID_ARG, "cf_warp_frame_and_codes: sign must be +-1");
     CF_REQUIRE((int64_t)H * W < (1ll << 30) && B <= 65535, CF_ERR_INVALID_ARG, "cf_warp_frame_and_codes: too large");
     if (B == 0) return CF_OK;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    WarpJob ji, jz;
-    if (int rc = make_job(ji, img, img_out, Ci, H, W, H, W, 1)) return rc;
-    if (int rc = make_job(jz, codes, codes_out, Cz, H / 2, W / 2, H, W, 8)) return rc;
-    {
-        const int rc = launch_staged(ji, true, jz, flow, H, W, sign, B, gate, stream);
-        if (rc != 1) return rc;
-    }
-    dim3 grid(ji.blocks_x * ji.groups + jz.blocks_x * jz.groups, B);
-    warp_frame_and_codes_kernel<<<grid, 256, 0, stream>>>(ji, jz, flow, H, W, sign, gate);
-    CF_LAUNCH_CHECK("warp_frame_and_codes_kernel");
-    return CF_OK;
+    return warp_frame_and_codes_impl(img, codes, flow, img_out, codes_out, B, Ci, Cz, H, W, sign, gate, FlowLR{},
+                                     (cudaStream_t)stream_);
+}
+
+extern "C" int cf_warp_frame_and_codes_upflow8(const float *img, const float *codes, const float *flow_lr, float *img_out,
+                                               float *codes_out, float *flow_out, int B, int Ci, int Cz, int H, int W,
+                                               int lh, int lw, int pad_h, int pad_w, float sign, cf_stream_t stream_) {
+    using namespace cf;
+    if (int rc = check_device()) return rc;
+    CF_REQUIRE(img && codes && flow_lr && img_out && codes_out, CF_ERR_NULL, "cf_warp_frame_and_codes_upflow8: null pointer");
+    CF_REQUIRE(B >= 0 && Ci > 0 && Cz > 0 && H > 1 && W > 1 && lh > 0 && lw > 0, CF_ERR_INVALID_ARG,
+               "cf_warp_frame_and_codes_upflow8: bad shape B=%d Ci=%d Cz=%d H=%d W=%d lh=%d lw=%d", B, Ci, Cz, H, W, lh, lw);
+    CF_REQUIRE(pad_h >= 0 && pad_w >= 0 && 8 * lh - pad_h == H && 8 * lw - pad_w == W, CF_ERR_INVALID_ARG,
+               "cf_warp_frame_and_codes_upflow8: 8*[%d,%d] minus the top/left padding [%d,%d] is not the frame [%d,%d]", lh, lw,
+               pad_h, pad_w, H, W);
+    CF_REQUIRE(sign == 1.f || sign == -1.f, CF_ERR_INVALID_ARG, "cf_warp_frame_and_codes_upflow8: sign must be +-1");
+    CF_REQUIRE((int64_t)H * W < (1ll << 30) && B <= 65535, CF_ERR_INVALID_ARG, "cf_warp_frame_and_codes_upflow8: too large");
+    if (B == 0) return CF_OK;
+    FlowLR lr;
+    lr.lr = flow_lr; lr.lh = lh; lr.lw = lw; lr.pad_h = pad_h; lr.pad_w = pad_w;
+    lr.sy = 8 * lh > 1 ? (float)(lh - 1) / (float)(8 * lh - 1) : 0.f;   // ATen area_pixel_compute_scale, align_corners
+    lr.sx = 8 * lw > 1 ? (float)(lw - 1) / (float)(8 * lw - 1) : 0.f;
+    lr.flow_out = flow_out;
+    // (no zero-flow gate here: the reference's predicate is on the up-sampled flow, which this call never materialises
+    //  before warping; callers that need the branch use cf_flow_any on flow_out of the previous step or the unfused calls)
+    return warp_frame_and_codes_impl(img, codes, flow_lr /*unused*/, img_out, codes_out, B, Ci, Cz, H, W, sign, nullptr, lr,
+                                     (cudaStream_t)stream_);
 }

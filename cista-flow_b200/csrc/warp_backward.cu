@@ -54,7 +54,7 @@ warp_backward_kernel(const float *__restrict__ grad_out, const float *__restrict
     if (p >= plane) return;
     const int y = p / W, x = p - y * W;
     const float *fb = flow + (size_t)b * 2 * fH * fW;
-    const float2 uv = flow_at(fb, x, y, W, fH, fW, half != 0, sy, sx);
+    const float2 uv = flow_at(fb, x, y, W, fH, fW, half != 0, sy, sx, FlowLR{}, 0);
     const float gx = 2.f * (((float)x + sign * uv.x) / (float)W - 0.5f);
     const float gy = 2.f * (((float)y + sign * uv.y) / (float)H - 0.5f);
     float mx, my;

@@ -28,12 +28,46 @@ __device__ __forceinline__ float reflect_clip(float v, int size) {
     return fminf(span, fmaxf(r, 0.f));
 }
 
+// Fused upflow8 + ImagePadder.unpad (DCEIFlow/DCEIFlow.py:222-227, DCEIFlow/utils/sample_utils.py:66-68,
+// utils/image_process.py:87-107): the flow network predicts at 1/8 of the x32-padded frame; the reference up-samples
+// x8 bilinearly (align_corners=True, values x8), cuts the top/left padding off, and only then warps.  With `lr` set the
+// full-resolution flow is never read: it is evaluated from the 1/8-resolution field on the fly (and optionally written
+// out once, by the image part, because the model returns it as batch_flow['flow_final']).
+struct FlowLR {
+    const float *lr;       // [B,2,lh,lw] or nullptr (no fused up-sampling: the kernels read `flow`)
+    int lh, lw, pad_h, pad_w;
+    float sy, sx;          // ATen align_corners scales (lh-1)/(8*lh-1), (lw-1)/(8*lw-1)
+    float *flow_out;       // optional [B,2,H,W]: upflow8 + unpad
+};
+
+// ATen upsample_bilinear2d(align_corners=True) at destination (X, Y) of the x8 grid, times 8; (x, y) un-padded
+static __device__ __noinline__ float2 upflow8_at(const FlowLR &s, int b, int x, int y) {
+    const float fy = s.sy * (float)(y + s.pad_h), fx = s.sx * (float)(x + s.pad_w);
+    const int y0 = min((int)fy, s.lh - 1), x0 = min((int)fx, s.lw - 1);
+    const int y1 = y0 + (y0 < s.lh - 1 ? 1 : 0), x1 = x0 + (x0 < s.lw - 1 ? 1 : 0);
+    const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float *c = s.lr + (size_t)b * 2 * s.lh * s.lw;
+    float2 r;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float p00 = __ldg(c + y0 * s.lw + x0), p01 = __ldg(c + y0 * s.lw + x1);
+        const float p10 = __ldg(c + y1 * s.lw + x0), p11 = __ldg(c + y1 * s.lw + x1);
+        const float v = 8.f * (ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11));
+        if (k == 0) r.x = v; else r.y = v;
+        c += (size_t)s.lh * s.lw;
+    }
+    return r;
+}
+
 // Flow at output pixel (x, y).  half == false: flow has the output's size.
 // half == true: x0.5 bilinear, align_corners=True from the [fH, fW] field
 // (ATen upsample_bilinear2d: src = scale*dst, lambda clamped to [0,1]).
+// `fb` is this batch item's [2,fH,fW] field; with lr.lr set the field is virtual (upflow8_at).
 __device__ __forceinline__ float2 flow_at(const float *__restrict__ fb, int x, int y, int W,
-                                          int fH, int fW, bool half, float sy, float sx) {
+                                          int fH, int fW, bool half, float sy, float sx, const FlowLR &lr, int b) {
     if (!half) {
+        if (lr.lr) return upflow8_at(lr, b, x, y);
         const int p = y * W + x;
         return make_float2(__ldg(fb + p), __ldg(fb + (size_t)fH * fW + p));
     }
@@ -43,6 +77,13 @@ __device__ __forceinline__ float2 flow_at(const float *__restrict__ fb, int x, i
     const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
     const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
     float2 r;
+    if (lr.lr) {
+        const float2 p00 = upflow8_at(lr, b, x0, y0), p01 = upflow8_at(lr, b, x1, y0);
+        const float2 p10 = upflow8_at(lr, b, x0, y1), p11 = upflow8_at(lr, b, x1, y1);
+        r.x = ly0 * (lx0 * p00.x + lx1 * p01.x) + ly1 * (lx0 * p10.x + lx1 * p11.x);
+        r.y = ly0 * (lx0 * p00.y + lx1 * p01.y) + ly1 * (lx0 * p10.y + lx1 * p11.y);
+        return r;
+    }
     const float *c = fb;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -166,7 +207,8 @@ constexpr int kTileW = 32, kTileH = 8;
 
 template <int CPT>
 __device__ __forceinline__ void run_job(const WarpJob &j, const float *__restrict__ flow,
-                                        int fH, int fW, float sign, int tile, int group, int b, const int *__restrict__ gate) {
+                                        int fH, int fW, float sign, int tile, int group, int b, const int *__restrict__ gate,
+                                        const FlowLR &lr, bool write_flow = false) {
     const int ty = tile / j.tiles_x, tx = tile - ty * j.tiles_x;
     const int x = tx * kTileW + (threadIdx.x & 31), y = ty * kTileH + (threadIdx.x >> 5);
     if (x >= j.W || y >= j.H) return;
@@ -176,7 +218,12 @@ __device__ __forceinline__ void run_job(const WarpJob &j, const float *__restric
     if (gate_closed(gate)) {
         t = identity_taps(x, y, j.W);
     } else {
-        const float2 uv = flow_at(fb, x, y, j.W, fH, fW, j.half != 0, j.sy, j.sx);
+        const float2 uv = flow_at(fb, x, y, j.W, fH, fW, j.half != 0, j.sy, j.sx, lr, b);
+        if (write_flow && lr.flow_out != nullptr && group == 0) {   // upflow8 + unpad, once per full-resolution pixel
+            float *fo = lr.flow_out + (size_t)b * 2 * j.H * j.W;
+            fo[p] = uv.x;
+            fo[(size_t)j.H * j.W + p] = uv.y;
+        }
         t = make_taps(uv.x, uv.y, x, y, j.H, j.W, sign);
     }
     const size_t plane = (size_t)j.H * j.W;

@@ -54,7 +54,7 @@ constexpr int CH_PER_CTA = 64;           // channel group of one CTA (8 stages o
 // One 32x32 block of the (few-channel, full-resolution) image: thread <-> 4 rows; all flow loads, then all 16 tap
 // loads, then the stores (one pixel per thread cost two dependent DRAM round trips per 256 pixels).
 __device__ __forceinline__ void warp_image_block(const WarpJob &ji, const float *__restrict__ flow, int fH, int fW, float sign,
-                                                 bool identity, int b, int bx0, int by0) {
+                                                 bool identity, int b, int bx0, int by0, const FlowLR &lr) {
     const int Hi = ji.H, Wi = ji.W;
     const size_t hw = (size_t)Hi * Wi;
     const float *fbi = flow + (size_t)b * 2 * fH * fW;  // image resolution == flow resolution
@@ -66,8 +66,19 @@ __device__ __forceinline__ void warp_image_block(const WarpJob &ji, const float 
     for (int k = 0; k < 4; ++k) {
         yy[k] = by0 + (int)(threadIdx.x >> 5) + 8 * k;
         const int yc = min(yy[k], Hi - 1);
-        fu[k] = __ldg(fbi + (size_t)yc * Wi + xc);
-        fv[k] = __ldg(fbi + hw + (size_t)yc * Wi + xc);
+        if (lr.lr) {   // fused upflow8 + unpad; the image part also writes the up-sampled flow out (once per pixel)
+            const float2 uv = upflow8_at(lr, b, xc, yc);
+            fu[k] = uv.x;
+            fv[k] = uv.y;
+            if (lr.flow_out != nullptr && x < Wi && yy[k] < Hi) {
+                float *fo = lr.flow_out + (size_t)b * 2 * hw;
+                st_cs(fo + (size_t)yc * Wi + xc, uv.x);
+                st_cs(fo + hw + (size_t)yc * Wi + xc, uv.y);
+            }
+        } else {
+            fu[k] = __ldg(fbi + (size_t)yc * Wi + xc);
+            fv[k] = __ldg(fbi + hw + (size_t)yc * Wi + xc);
+        }
     }
     Taps t[4];
 #pragma unroll
@@ -122,7 +133,8 @@ __device__ __forceinline__ bool elect_lane() {
 template <bool QUAD>
 __global__ void __launch_bounds__(256, 3)
 warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_in_tiles, WarpJob jz, int tiles_x, int tiles,
-                int groups, const float *__restrict__ flow, int fH, int fW, float sign, const int *__restrict__ gate) {
+                int groups, const float *__restrict__ flow, int fH, int fW, float sign, const int *__restrict__ gate,
+                const FlowLR lr) {
     using namespace wt;
     const bool identity = gate_closed(gate);  // device-side `not flow_final.any()` (e2v_model.py:184): copy
     const int b = blockIdx.y;
@@ -151,7 +163,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
             by0 = 32 * ty;
         }
 #pragma unroll 1
-        for (int k = 0; k < n_blocks; ++k) warp_image_block(ji, flow, fH, fW, sign, identity, b, bx0 + 32 * k, by0);
+        for (int k = 0; k < n_blocks; ++k) warp_image_block(ji, flow, fH, fW, sign, identity, b, bx0 + 32 * k, by0, lr);
         if (image_cta) return;
     }
 
@@ -189,7 +201,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
             if (identity) {
                 taps[k] = identity_taps(x, y, W);
             } else {
-                const float2 uv = flow_at(fb, x, y, W, fH, fW, jz.half != 0, jz.sy, jz.sx);
+                const float2 uv = flow_at(fb, x, y, W, fH, fW, jz.half != 0, jz.sy, jz.sx, lr, b);
                 taps[k] = make_taps(uv.x, uv.y, x, y, H, W, sign);
             }
             y0a[k] = taps[k].o00 / W;
@@ -328,7 +340,7 @@ warp_tma_kernel(const __grid_constant__ CUtensorMap tmap, WarpJob ji, int image_
 }
 
 int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const float *flow, int fH, int fW, float sign,
-                    int B, const int *gate, cudaStream_t stream) {
+                    int B, const int *gate, const FlowLR &lr, cudaStream_t stream) {
     using namespace wt;
     static const char *env = getenv("CF_WARP_PATH");  // experiments: "direct" forces the plain gather
     const bool disabled = env && !strcmp(env, "direct");
@@ -386,9 +398,9 @@ int launch_warp_tma(const WarpJob &ji, bool with_image, const WarpJob &jz, const
     const int n_img = (with_image && !in_tiles) ? (int)(ceil_div(ji.W, 32) * ceil_div(ji.H, 32)) : 0;
     dim3 grid((unsigned)(n_img + tiles * groups), (unsigned)B);
     if (quad)
-        warp_tma_kernel<true><<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, in_tiles ? 1 : 0, jz, tiles_x, tiles, groups, flow, fH, fW, sign, gate);
+        warp_tma_kernel<true><<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, in_tiles ? 1 : 0, jz, tiles_x, tiles, groups, flow, fH, fW, sign, gate, lr);
     else
-        warp_tma_kernel<false><<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, in_tiles ? 1 : 0, jz, tiles_x, tiles, groups, flow, fH, fW, sign, gate);
+        warp_tma_kernel<false><<<grid, 256, SMEM_BYTES, stream>>>(tmap, ji, in_tiles ? 1 : 0, jz, tiles_x, tiles, groups, flow, fH, fW, sign, gate, lr);
     CF_LAUNCH_CHECK("warp_tma_kernel");
     return CF_OK;
 }

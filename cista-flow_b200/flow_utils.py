@@ -134,6 +134,36 @@ def warp_frame_and_codes(img: torch.Tensor, codes: torch.Tensor, flow: torch.Ten
     return img_out, codes_out
 
 
+def warp_frame_and_codes_upflow8(img: torch.Tensor, codes: torch.Tensor, flow_lr: torch.Tensor, mode: str = "forward",
+                                 pad: tuple[int, int] | None = None, return_flow: bool = True):
+    """The whole tail of the reference's frame step in ONE launch: ``upflow8`` of the flow network's
+    1/8-resolution output (DCEIFlow/utils/sample_utils.py:66-68), ``ImagePadder.unpad`` (utils/image_process.py:103-107),
+    warp of the previous frame, x0.5 down-sampling of the flow and warp of the sparse codes (e2v/e2v_model.py:188-191).
+
+    img [B,Ci,H,W], codes [B,Cz,H//2,W//2], flow_lr [B,2,lh,lw] with 8*lh = H + pad_h, 8*lw = W + pad_w (top/left
+    padding; ``pad`` defaults to what ImagePadder(min_size=32) adds).  Returns (warped image, warped codes, flow_final
+    [B,2,H,W] or None)."""
+    img, codes, flow_lr = _prep(img, "img"), _prep(codes, "codes"), _prep(flow_lr, "flow_lr")
+    B, Ci, H, W = img.shape
+    lh, lw = flow_lr.shape[2], flow_lr.shape[3]
+    if pad is None:
+        pad = (8 * lh - H, 8 * lw - W)
+    pad_h, pad_w = int(pad[0]), int(pad[1])
+    assert flow_lr.shape[:2] == (B, 2) and 8 * lh - pad_h == H and 8 * lw - pad_w == W, \
+        "flow_lr must be [B,2,(H+pad_h)/8,(W+pad_w)/8]"
+    assert codes.shape[0] == B and codes.shape[2] == H // 2 and codes.shape[3] == W // 2, "codes must be [B,C,H//2,W//2]"
+    img_out, codes_out = torch.empty_like(img), torch.empty_like(codes)
+    flow_out = torch.empty((B, 2, H, W), dtype=torch.float32, device=img.device) if return_flow else None
+    sign = -1.0 if mode == "forward" else 1.0
+    lib = _lib.load()
+    with torch.cuda.device(img.device):
+        rc = lib.cf_warp_frame_and_codes_upflow8(img.data_ptr(), codes.data_ptr(), flow_lr.data_ptr(), img_out.data_ptr(),
+                                                 codes_out.data_ptr(), _lib.ptr(flow_out), B, Ci, codes.shape[1], H, W, lh, lw,
+                                                 pad_h, pad_w, sign, _lib.stream_ptr(img.device))
+    _lib.check(rc, "cf_warp_frame_and_codes_upflow8")
+    return img_out, codes_out, flow_out
+
+
 class backWarp(nn.Module):
     """I0 = backwarp(I1, F_0_1): gather at (x+u, y+v)  (utils/flow_utils.py:40-120).
     Note the (W, H) argument order of the reference."""

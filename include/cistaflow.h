@@ -181,6 +181,19 @@ CF_API int cf_warp_frame_and_codes_gated(const float *img, const float *codes, c
                                   float *img_out, float *codes_out, int B, int Ci, int Cz,
                                   int H, int W, float sign, const int *gate, cf_stream_t stream);
 
+/* The frame step from the flow network's own output (completed in round 2): DCEIFlow
+ * predicts the flow at 1/8 of the x32-padded frame; the reference up-samples it with upflow8
+ * (DCEIFlow/DCEIFlow.py:222, DCEIFlow/utils/sample_utils.py:66-68: x8 bilinear, align_corners=True, values x8), cuts the
+ * top/left padding off (ImagePadder.unpad, utils/image_process.py:103-107), and only then warps the previous frame and
+ * -- after another x0.5 bilinear down-sampling -- the sparse codes (e2v/e2v_model.py:188-191).  One launch does all of it:
+ *   flow_lr   [B,2,lh,lw]  coords1 - coords0 of the last refinement iteration, lh = (H + pad_h)/8, lw = (W + pad_w)/8
+ *   flow_out  [B,2,H,W] or NULL: the up-sampled, un-padded flow (what the model returns as batch_flow['flow_final'])
+ *   img [B,Ci,H,W], codes [B,Cz,H/2,W/2] and their outputs as in cf_warp_frame_and_codes.
+ * Same arithmetic, operation by operation, as the reference's three ATen calls followed by cf_warp_frame_and_codes. */
+CF_API int cf_warp_frame_and_codes_upflow8(const float *img, const float *codes, const float *flow_lr, float *img_out,
+                                    float *codes_out, float *flow_out, int B, int Ci, int Cz, int H, int W,
+                                    int lh, int lw, int pad_h, int pad_w, float sign, cf_stream_t stream);
+
 /* Adjoint of cf_warp: what autograd runs through forwardWarp / backWarp in
  * training (loss.py:147,336,398; train.py:208-232).  grad_out [B,C,H,W];
  *   grad_img  [B,C,H,W]           <- bilinear SPLAT of grad_out into the 4 taps (may be NULL)

@@ -235,6 +235,21 @@ def warp_frame_and_codes(img, codes, flow, mode="forward"):
     return warp(img, flow, mode), warp(codes, downsample_flow(flow), mode)
 
 
+def upflow8_unpad(flow_lr: torch.Tensor, pad_h: int, pad_w: int) -> torch.Tensor:
+    """DCEIFlow/utils/sample_utils.py:66-68 (``8 * F.interpolate(size=8x, bilinear, align_corners=True)``) followed by
+    ``ImagePadder.unpad`` (utils/image_process.py:103-107: the padding sits on the top/left): DCEIFlow/DCEIFlow.py:222-227."""
+    h, w = flow_lr.shape[-2:]
+    up = 8 * F.interpolate(flow_lr, size=(8 * h, 8 * w), mode="bilinear", align_corners=True)
+    return up[..., pad_h:, pad_w:]
+
+
+def warp_frame_and_codes_upflow8(img, codes, flow_lr, pad_h: int, pad_w: int, mode="forward"):
+    """upflow8 + unpad + the per-frame warp step (e2v/e2v_model.py:188-191): (warped image, warped codes, flow_final)."""
+    flow = upflow8_unpad(flow_lr, pad_h, pad_w).contiguous()
+    wi, wz = warp_frame_and_codes(img, codes, flow, mode)
+    return wi, wz, flow
+
+
 # --------------------------------------------------------------------------
 # part 3: all-pairs correlation + pyramid lookup   (ERAFT/corr.py == DCEIFlow/core/corr/raft_corr.py)
 # --------------------------------------------------------------------------

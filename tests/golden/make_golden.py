@@ -125,6 +125,20 @@ def make_warp():
     out["step/codes_warped"] = fw.warp_frame(torch.from_numpy(z1), ds).numpy()
     bw = FrameWarp("backward")
     out["step/codes_warped_backward"] = bw.warp_frame(torch.from_numpy(z1), ds).numpy()
+
+    # the same step from the flow network's 1/8-resolution output: upflow8 (DCEIFlow/utils/sample_utils.py:66-68) +
+    # ImagePadder.unpad (utils/image_process.py:103-107, padding on the top/left) + the warps
+    from DCEIFlow.utils.sample_utils import upflow8
+    from utils.image_process import ImagePadder
+    padder = ImagePadder((36, 44), min_size=32)
+    lr = (0.6 * np.random.default_rng(23).standard_normal((1, 2, 8, 8))).astype(np.float32)     # (36+28)/8 x (44+20)/8
+    up = padder.unpad(upflow8(torch.from_numpy(lr)))
+    assert tuple(up.shape) == (1, 2, 36, 44) and (padder.pad_height, padder.pad_width) == (28, 20)
+    ds8 = torch.nn.functional.interpolate(up, scale_factor=0.5, mode="bilinear", align_corners=True)
+    out["up8/flow_lr"], out["up8/pad"] = lr, np.array([padder.pad_height, padder.pad_width])
+    out["up8/flow_final"] = up.numpy().copy()
+    out["up8/img_warped"] = fw.warp_frame(torch.from_numpy(i1), up).numpy()
+    out["up8/codes_warped"] = fw.warp_frame(torch.from_numpy(z1), ds8).numpy()
     save("warp.npz", **out)
 
 

@@ -160,3 +160,41 @@ def test_multi_frame_trace_replay(golden, cuda_device, parity_report, trace):
         np.testing.assert_allclose(sep.cpu().numpy(), g[f"f{f}/warp0_out"], rtol=0, atol=1e-4)
     parity_report.add("multi_frame_trace_replay", trace=trace, frames=frames, max_lookup_err_over_max=worst["lookup"],
                       max_warp_abs_err=worst["warp"], max_fused_voxel_abs_err=worst["voxel"])
+
+
+# ------------------------------------------------ fused upflow8 + unpad + warp ---
+def test_upflow8_unpad_warp_golden(golden, cuda_device):
+    """One launch for upflow8 + ImagePadder.unpad + frame warp + x0.5 flow + codes warp, against the reference's own
+    outputs (tests/golden/warp.npz up8/*: DCEIFlow/utils/sample_utils.py:66-68, utils/image_process.py:103-107)."""
+    g = golden("warp")
+    pad = tuple(int(v) for v in g["up8/pad"])
+    n0 = cf.load_library().cf_launch_count()
+    wi, wz, flow = cf.warp_frame_and_codes_upflow8(dev_t(g["step/img"], cuda_device), dev_t(g["step/codes"], cuda_device),
+                                                   dev_t(g["up8/flow_lr"], cuda_device), "forward", pad=pad)
+    assert cf.load_library().cf_launch_count() - n0 == 1
+    np.testing.assert_allclose(flow.cpu().numpy(), g["up8/flow_final"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(wi.cpu().numpy(), g["up8/img_warped"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(wz.cpu().numpy(), g["up8/codes_warped"], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("h,w,batch,channels", [(180, 240, 2, 128), (260, 346, 1, 128), (480, 640, 1, 128), (36, 44, 3, 6)])
+@pytest.mark.parametrize("mode", ["forward", "backward"])
+def test_upflow8_unpad_warp_vs_oracle(cuda_device, h, w, batch, channels, mode):
+    """Config shapes (x32 padding on the top/left like ImagePadder): staged (TMA) and direct kernels, both warp modes."""
+    img, codes, _ = synth.warp_inputs(batch, h, w, seed=31, code_channels=channels, flow_kind="smooth")
+    hp, wp = synth.padded_dims(h, w)
+    pad = (hp - h, wp - w)
+    rng = np.random.default_rng(32)
+    lr = synth.smooth_field(rng, batch, 2, hp // 8, wp // 8, 0.35, cell=4)      # x8 -> a few px, like the model's flow
+    ri, rz, rf = ref_port.warp_frame_and_codes_upflow8(torch.from_numpy(img), torch.from_numpy(codes), torch.from_numpy(lr),
+                                                       pad[0], pad[1], mode)
+    wi, wz, wf = cf.warp_frame_and_codes_upflow8(dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(lr, cuda_device),
+                                                 mode, pad=pad)
+    assert (wf.cpu() - rf).abs().max().item() <= 1e-5
+    assert (wi.cpu() - ri).abs().max().item() <= 1e-4 and (wz.cpu() - rz).abs().max().item() <= 1e-4
+    # ... and identical to the unfused calls on the up-sampled flow
+    ui, uz = cf.warp_frame_and_codes(dev_t(img, cuda_device), dev_t(codes, cuda_device), wf, mode)
+    assert (ui - wi).abs().max().item() <= 1e-6 and (uz - wz).abs().max().item() <= 1e-6
+    with pytest.raises(ValueError):
+        cf.warp_frame_and_codes_upflow8(dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(lr, cuda_device), mode,
+                                        pad=(pad[0] + 8, pad[1]))

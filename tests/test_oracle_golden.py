@@ -213,3 +213,13 @@ def test_multi_frame_trace_through_oracle(golden, trace):
         assert ev.shape == (nev, 4) and np.all(np.diff(ev[:, 0]) >= 0)
     # the recurrence is live: consecutive frames warp different states with different flows
     assert not np.array_equal(g["f0/warp1_in"], g["f1/warp1_in"]) and not np.array_equal(g["f0/flow_final"], g["f1/flow_final"])
+
+
+def test_upflow8_unpad_warp_step(golden):
+    """upflow8 + ImagePadder.unpad + warps (DCEIFlow.py:222-227, e2v_model.py:188-191): oracle port == reference."""
+    g = golden("warp")
+    pad_h, pad_w = (int(v) for v in g["up8/pad"])
+    wi, wz, flow = ref_port.warp_frame_and_codes_upflow8(torch.from_numpy(g["step/img"]), torch.from_numpy(g["step/codes"]),
+                                                         torch.from_numpy(g["up8/flow_lr"]), pad_h, pad_w, "forward")
+    assert np.array_equal(flow.numpy(), g["up8/flow_final"])
+    assert np.array_equal(wi.numpy(), g["up8/img_warped"]) and np.array_equal(wz.numpy(), g["up8/codes_warped"])
