@@ -53,6 +53,12 @@ namespace tc {
 
 constexpr int BM = 128;          // queries per tile (UMMA M)
 constexpr int BK = 32;           // K rows per pipeline stage (4 MMAs of K=8)
+// fp16 operands: 64 K rows per stage.  One SM's TMA unit retires a 3-D box instruction of these shapes about every
+// 320 ns WHATEVER its size between 20 and 40 KB (profiles/r02/tma_probe.txt: {64 cols, 32 rows, 5 atoms} and
+// {64, 64, 5} both 320 ns), and a stage is two instructions (fmap1 box + fmap2 box): with 32-row stages the fp16
+// kernel spent 8 x 2 x 320 ns = 5.1 us per tile on operand loads alone -- exactly what it measured, and why halving
+// the operand bytes had bought nothing in round 1.  Four 64-row stages are 2.6 us.
+constexpr int BK_F16 = 64;
 constexpr int MAX_STAGES = 8;     // ring depth = as many stages of (fmap1 tile + this shape's fmap2 tile) as fit, at most 6
 constexpr int MAX_BN = 256;      // UMMA N limit
 constexpr int BOX_BYTES = 32 * 32 * 4;                 // one TMA box: 32 cols x 32 rows fp32
@@ -387,8 +393,10 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int EPI_SPLIT = ES, EPI_WARPS = 4 * ES, EPI_BYTES = epi_bytes(ES);
     constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
     constexpr int BC = F16 ? 64 : 32;                   // operand columns per TMA box (128 bytes)
-    constexpr int ABYTES = (BM / BC) * BOX_BYTES;       // fmap1 part of a stage
-    constexpr int MMAS = F16 ? BK / 16 : BK / 8;        // MMAs per stage
+    constexpr int BKK = F16 ? BK_F16 : BK;              // K rows per stage
+    constexpr int BOXB = 128 * BKK;                     // bytes of one TMA box: 128-byte rows x BKK
+    constexpr int ABYTES = (BM / BC) * BOXB;            // fmap1 part of a stage
+    constexpr int MMAS = F16 ? BKK / 16 : BKK / 8;      // MMAs per stage
     constexpr int KSTEP = F16 ? 2048 : 1024;            // descriptor start-address advance per MMA
     const int STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
     uint8_t *epi = smem + STAGES * STAGE_BYTES;  // [EPI_WARPS][2][EPI_BUF_BYTES]
@@ -398,7 +406,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kblocks = p.D / BK;
+    const int kblocks = p.D / BKK;
     const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
     const int first_tile = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
     if (threadIdx.x == 0) stamp(0);
@@ -434,7 +442,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             // pair kernel: the leader's barrier counts the bytes of BOTH CTAs' boxes
-            const uint32_t tx_bytes = (uint32_t)(CL * (BM / BC + (CL == 2 ? p.b_half : p.n_boxes_b))) * BOX_BYTES;
+            const uint32_t tx_bytes = (uint32_t)(CL * (BM / BC + (CL == 2 ? p.b_half : p.n_boxes_b))) * BOXB;
             const int jr = CL == 2 ? rank * (p.BN_mma / 2) : 0;  // first fmap2 column of this CTA inside the tile
             int tile_no = 0;
             for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
@@ -449,7 +457,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         if (kb == kblocks - 1) TC_TRACE(tile_no, 1);
                     }
                     uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + ABYTES;
-                    const int krow = b * p.D + kb * BK;
+                    const int krow = b * p.D + kb * BKK;
                     const bool issuer = elect_one();
                     if (!issuer) {
                         __syncwarp();
@@ -485,12 +493,12 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         tma_load_3d(sa, &tmap_a, 0, krow, i0 / BC, &full[stage]);
                     } else {
 #pragma unroll
-                        for (int a = 0; a < BM / BC; ++a) tma_load_2d(sa + a * BOX_BYTES, &tmap_a, i0 + BC * a, krow, &full[stage]);
+                        for (int a = 0; a < BM / BC; ++a) tma_load_2d(sa + a * BOXB, &tmap_a, i0 + BC * a, krow, &full[stage]);
                     }
                     if (p.b3d) {
                         tma_load_3d(sb, &tmap_b, 0, krow, j0 / BC, &full[stage]);
                     } else {
-                        for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOX_BYTES, &tmap_b, j0 + BC * a, krow, &full[stage]);
+                        for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOXB, &tmap_b, j0 + BC * a, krow, &full[stage]);
                     }
                     if (tile == first_tile && kb == 0) stamp(2);
                     __syncwarp();
@@ -511,7 +519,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // descriptor high words are constants of the layout; the low word = start address >> 4 | LBO << 16
             const uint32_t desc_hi = F16 ? (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29))
                                          : (uint32_t)((512u >> 4) | (1u << 14) | (1u << 29));
-            const uint32_t lbo_bits = (4096u >> 4) << 16;
+            const uint32_t lbo_bits = ((uint32_t)BOXB >> 4) << 16;   // bytes between column atoms = one TMA box
             const uint32_t smem_base = smem_u32(smem);
             int tile_no = 0;
             for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
@@ -839,9 +847,12 @@ CF_DEFINE_TRACE_SETTER(cf_trace_buffer_corr)
 // amax[t * B + b] = max |x| over batch item b of feature map t (t = 0, 1), as the bit pattern of a non-negative float
 // (integer max == float max); zeroed by the host side before the launch.
 __global__ void __launch_bounds__(256)
-fmap_absmax_kernel(const float *__restrict__ f1, const float *__restrict__ f2, int64_t per_item, int B, unsigned *__restrict__ amax) {
-    const int item = blockIdx.y;                       // t * B + b
-    const float *src = (item < B ? f1 : f2) + (int64_t)(item < B ? item : item - B) * per_item;
+fmap_absmax_kernel(const float *__restrict__ f1, const float *__restrict__ f2, int64_t per_item, int B, int b0, int nbc,
+                   unsigned *__restrict__ amax) {
+    // this launch covers batch items [b0, b0 + nbc) of both maps: blockIdx.y = t * nbc + (b - b0)
+    const int t = (int)blockIdx.y / nbc, b = b0 + (int)blockIdx.y % nbc;
+    const int item = t * B + b;
+    const float *src = (t == 0 ? f1 : f2) + (int64_t)b * per_item;
     float m = 0.f;
     const int64_t n4 = per_item >> 2;
     const float4 *s4 = reinterpret_cast<const float4 *>(src);
@@ -862,12 +873,13 @@ fmap_absmax_kernel(const float *__restrict__ f1, const float *__restrict__ f2, i
 // input fits fp16 (round to nearest: the same 11-bit significand a TF32 operand keeps), the scaling is exact, and
 // inv_scale[item] = 2^-shift lets the GEMM epilogue undo it.  per_item % 4 == 0.
 __global__ void __launch_bounds__(256)
-fmap_to_half_kernel(const float *__restrict__ f1, const float *__restrict__ f2, int64_t per_item, int B,
+fmap_to_half_kernel(const float *__restrict__ f1, const float *__restrict__ f2, int64_t per_item, int B, int b0, int nbc,
                     const unsigned *__restrict__ amax, __half *__restrict__ h1, __half *__restrict__ h2,
                     float *__restrict__ inv_scale) {
-    const int item = blockIdx.y;
-    const bool first = item < B;
-    const int64_t base = (int64_t)(first ? item : item - B) * per_item;
+    const int t = (int)blockIdx.y / nbc, b = b0 + (int)blockIdx.y % nbc;
+    const int item = t * B + b;
+    const bool first = t == 0;
+    const int64_t base = (int64_t)b * per_item;
     const float *src = (first ? f1 : f2) + base;
     __half *dst = (first ? h1 : h2) + base;
     const float mx = __uint_as_float(__ldg(amax + item));
@@ -982,6 +994,7 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // TF32 to summation-order noise (same 11-bit operand significands), but measured NO faster on the B200
     // (8 x 60x80: GEMM 283 against 277 us, plus 32 us of conversion) -- the kernel is bound on the volume's write side
     if (precision == CF_CORR_AUTO) precision = CF_CORR_TF32;
+    if (precision == CF_CORR_F16 && D % BK_F16 != 0) precision = CF_CORR_TF32;   // the fp16 stages hold 64 K rows
     const bool f16 = precision == CF_CORR_F16;
     const int BC = f16 ? 64 : 32;   // operand columns per TMA box
     const void *a = f1, *bm = f2;
@@ -997,15 +1010,23 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         unsigned *amax = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(ws) + 2 * per_map);
         float *inv = reinterpret_cast<float *>(amax + 2 * B);
         CF_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned) * 2 * B, stream));
-        int64_t bx = ceil_div(per_item / 4, 256 * 8);
-        const int64_t cap = ceil_div(8 * (int64_t)sm_count(), 2 * B);
-        if (bx > cap) bx = cap;
-        if (bx < 1) bx = 1;
-        dim3 grid((unsigned)bx, (unsigned)(2 * B));
-        fmap_absmax_kernel<<<grid, 256, 0, stream>>>(f1, f2, per_item, B, amax);
-        CF_LAUNCH_CHECK("fmap_absmax_kernel");
-        fmap_to_half_kernel<<<grid, 256, 0, stream>>>(f1, f2, per_item, B, amax, h1, h2, inv);
-        CF_LAUNCH_CHECK("fmap_to_half_kernel");
+        // groups of batch items whose fp32 maps fit the L2 together (<= 48 MB): the conversion pass re-reads what the
+        // maximum pass just read out of L2, so the feature maps cross the HBM interface once, not twice
+        int nbc = (int)((48ll << 20) / (2 * per_item * (int64_t)sizeof(float)));
+        if (nbc < 1) nbc = 1;
+        if (nbc > B) nbc = B;
+        for (int b0 = 0; b0 < B; b0 += nbc) {
+            const int nb_ = B - b0 < nbc ? B - b0 : nbc;
+            int64_t bx = ceil_div(per_item / 4, 256 * 8);
+            const int64_t cap = ceil_div(8 * (int64_t)sm_count(), 2 * nb_);
+            if (bx > cap) bx = cap;
+            if (bx < 1) bx = 1;
+            dim3 grid((unsigned)bx, (unsigned)(2 * nb_));
+            fmap_absmax_kernel<<<grid, 256, 0, stream>>>(f1, f2, per_item, B, b0, nb_, amax);
+            CF_LAUNCH_CHECK("fmap_absmax_kernel");
+            fmap_to_half_kernel<<<grid, 256, 0, stream>>>(f1, f2, per_item, B, b0, nb_, amax, h1, h2, inv);
+            CF_LAUNCH_CHECK("fmap_to_half_kernel");
+        }
         a = h1; bm = h2; inv_scale = inv;
     }
     Params p{};
@@ -1056,12 +1077,17 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
                                        : ((flags & 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
     p.atoms3d = (N % BC == 0) && !(flags & 16);
     p.b3d = p.atoms3d && (p.BN % BC == 0 || p.tiles_n == 1);
-    const int a_bytes = (BM / BC) * BOX_BYTES;
-    p.stage_bytes = a_bytes + p.n_boxes_b * BOX_BYTES;
+    const int bk = f16 ? BK_F16 : BK;          // K rows per stage
+    const int boxb = 128 * bk;                 // bytes per TMA box
+    const int a_bytes = (BM / BC) * boxb;
+    p.stage_bytes = a_bytes + p.n_boxes_b * boxb;
     // two epilogue warps per TMEM lane quarter when the ring still gets >= 5 stages beside their 64 KB of buffers (fp16
     // operands); the deep pooling keeps per-thread row state and stays on one warp per quarter (flags bit7: force 1)
     // (measured slower again, also with the half-size fp16 stages: 396 against 359 us at 8 x 60x80 -- only on request)
-    const int es = (f16 && p.deep == 0 && (flags & 128) && (SMEM_LIMIT - smem_fixed(2)) / p.stage_bytes >= 5) ? 2 : 1;
+    // round 2: with 64-row fp16 stages the operand loads take 4 x 0.45 us and the MMAs 1.9 us per 128x160 tile; the
+    // epilogue on four warps (3.6 us per tile, corr_trace) became the critical path -> two warps per lane quarter by
+    // default for fp16 operands (flags bit7 now forces one)
+    const int es = (f16 && p.deep == 0 && !(flags & 128) && (SMEM_LIMIT - smem_fixed(2)) / p.stage_bytes >= 3) ? 2 : 1;
     p.stages = (SMEM_LIMIT - smem_fixed(es)) / p.stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     // pairs of query tiles as one 256-row UMMA across two CTAs: measured slower than one CTA per tile on the B200
@@ -1071,6 +1097,11 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // level-0 rows through the LSU instead of TMA bulk stores: helps where the operand loads already need many TMA
     // instructions per stage (N % 32 != 0: 64 x 36x44 398 -> 367 us), costs 2-5 % elsewhere (flags bit0: always TMA)
     p.lsu_stores = (!(flags & 1) && !p.atoms3d && N % 4 == 0) ? 1 : 0;
+    // round 2: one SM's TMA unit moves about one 128-byte box row per ns, loads and stores alike (profiles/r02/tma_probe.txt),
+    // and a 128x160 tile is 1280 operand rows + 640 level-0 rows: with fp16 operands the unit, not the tensor pipe or the
+    // HBM, was suspected to set the tile period.  Measured (flags bit5 routes the fp16 kernel's level-0 rows through the LSU):
+    // SLOWER, 64 x 60x80 2617 against 2515 us -- so bulk stores stay the default
+    if (f16 && N % 4 == 0 && (flags & 32)) p.lsu_stores = 1;
     // level-1 rows through shared memory into 64-byte runs (flags bit13: per-lane 16-byte stores): 64 x 24x32
     // 66.7 -> 60.8 us, 8 x 60x80 314 -> 309 us
     p.l1_staged = (p.R > 0 && p.w1 % 2 == 0 && !(flags & 8192)) ? 1 : 0;
@@ -1086,14 +1117,14 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     const int smem_bytes = p.stages * p.stage_bytes + smem_fixed(es);
     CUtensorMap ta, tb, tcm;
     if (p.atoms3d) {
-        if (int rc = make_fmap_tmap3(&ta, a, B, D, N, dt, BK, BM / BC)) return rc;
+        if (int rc = make_fmap_tmap3(&ta, a, B, D, N, dt, bk, BM / BC)) return rc;
     } else {
-        if (int rc = make_fmap_tmap(&ta, a, B, D, N, dt)) return rc;
+        if (int rc = make_fmap_tmap(&ta, a, B, D, N, dt, bk)) return rc;
     }
     if (p.b3d) {
-        if (int rc = make_fmap_tmap3(&tb, bm, B, D, N, dt, BK, pair ? p.b_half : p.n_boxes_b)) return rc;
+        if (int rc = make_fmap_tmap3(&tb, bm, B, D, N, dt, bk, pair ? p.b_half : p.n_boxes_b)) return rc;
     } else {
-        if (int rc = make_fmap_tmap(&tb, bm, B, D, N, dt)) return rc;
+        if (int rc = make_fmap_tmap(&tb, bm, B, D, N, dt, bk)) return rc;
     }
     if (int rc = make_volume_tmap(&tcm, level0, B, N)) return rc;
 

@@ -55,9 +55,9 @@ namespace cf {
 constexpr int kScatterThreads = 256;
 constexpr int kScatterUnroll = 4;
 
-__global__ void __launch_bounds__(kScatterThreads)
-voxel_scatter_atomic_kernel(const double *__restrict__ ev, const int64_t *__restrict__ off,
-                            int B, int nb, int H, int W, int flavour, float *__restrict__ out, int b_first, int b_end) {
+__device__ __forceinline__ void scatter_body(const double *__restrict__ ev, const int64_t *__restrict__ off,
+                                             int B, int nb, int H, int W, int flavour, float *__restrict__ out, int b_first,
+                                             int b_end, int blk, int nblk) {
     // the events of windows [b_first, b_end) (one L2-sized chunk of the batch), grid-stride over
     // tiles of 1024 events: the host does not know the chunk's event count (offsets are on the device)
     const int64_t ev_first = __ldg(off + b_first), ev_end = __ldg(off + b_end);
@@ -66,7 +66,7 @@ voxel_scatter_atomic_kernel(const double *__restrict__ ev, const int64_t *__rest
     constexpr int64_t kTileEvents = kScatterThreads * kScatterUnroll;
     Window w;
     w.b = -1;
-    for (int64_t tile = ev_first + (int64_t)blockIdx.x * kTileEvents; tile < ev_end; tile += (int64_t)gridDim.x * kTileEvents) {
+    for (int64_t tile = ev_first + (int64_t)blk * kTileEvents; tile < ev_end; tile += (int64_t)nblk * kTileEvents) {
         Event e[kScatterUnroll];
 #pragma unroll
         for (int k = 0; k < kScatterUnroll; ++k) {  // all loads in flight first
@@ -94,6 +94,12 @@ voxel_scatter_atomic_kernel(const double *__restrict__ ev, const int64_t *__rest
             if (b.bin + 1 < nb) atomicAdd(cell + planes_per_bin * plane, wr);
         }
     }
+}
+
+__global__ void __launch_bounds__(kScatterThreads)
+voxel_scatter_atomic_kernel(const double *__restrict__ ev, const int64_t *__restrict__ off,
+                            int B, int nb, int H, int W, int flavour, float *__restrict__ out, int b_first, int b_end) {
+    scatter_body(ev, off, B, nb, H, W, flavour, out, b_first, b_end, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ----------------------------------------- atomic mode, cluster (smem) path ---
@@ -532,10 +538,8 @@ constexpr int kStatThreads = 256;
 
 // Both kernels: one CTA = one chunk of a window; a thread streams its float4s with 4 loads in flight.
 // (Round-1a sized them for 296 CTAs with one load in flight per thread: 43 of 70 us at 8 x 480x640.)
-__global__ void __launch_bounds__(kStatThreads)
-voxel_stats_kernel(const float *__restrict__ grid, int64_t cells, int64_t chunk_len, float hot_thr,
-                   Partial *__restrict__ partials, int chunks) {
-    const int b = blockIdx.y, c = blockIdx.x;
+__device__ __forceinline__ void stats_body(const float *__restrict__ grid, int64_t cells, int64_t chunk_len, float hot_thr,
+                                           Partial *__restrict__ partials, int chunks, int b, int c) {
     const float *g = grid + (int64_t)b * cells;
     const int64_t s = (int64_t)c * chunk_len, e = min(cells, s + chunk_len);
     // short fp32 partials per thread (a few dozen terms), promoted to fp64 across threads and chunks
@@ -587,9 +591,14 @@ voxel_stats_kernel(const float *__restrict__ grid, int64_t cells, int64_t chunk_
 }
 
 __global__ void __launch_bounds__(kStatThreads)
-voxel_normalise_kernel(const float *in, float *out /* may alias in */, int64_t cells, int64_t chunk_len,
-                       float hot_thr, int mode, const Partial *__restrict__ partials, int chunks) {
-    const int b = blockIdx.y, c = blockIdx.x;
+voxel_stats_kernel(const float *__restrict__ grid, int64_t cells, int64_t chunk_len, float hot_thr,
+                   Partial *__restrict__ partials, int chunks) {
+    stats_body(grid, cells, chunk_len, hot_thr, partials, chunks, (int)blockIdx.y, (int)blockIdx.x);
+}
+
+__device__ __forceinline__ void normalise_body(const float *in, float *out /* may alias in */, int64_t cells, int64_t chunk_len,
+                                               float hot_thr, int mode, const Partial *__restrict__ partials, int chunks,
+                                               int b, int c) {
     const float *g = in + (int64_t)b * cells;
     float *o = out + (int64_t)b * cells;
     const int64_t s = (int64_t)c * chunk_len, e = min(cells, s + chunk_len);
@@ -670,6 +679,51 @@ voxel_normalise_kernel(const float *in, float *out /* may alias in */, int64_t c
     }
 }
 
+__global__ void __launch_bounds__(kStatThreads)
+voxel_normalise_kernel(const float *in, float *out /* may alias in */, int64_t cells, int64_t chunk_len,
+                       float hot_thr, int mode, const Partial *__restrict__ partials, int chunks) {
+    normalise_body(in, out, cells, chunk_len, hot_thr, mode, partials, chunks, (int)blockIdx.y, (int)blockIdx.x);
+}
+
+// ---------------------------------------------------------- pipelined launches ---
+// The four stages of the L2-atomic path (zero, scatter, statistics, normalise) of FOUR consecutive window chunks in ONE
+// launch: CTAs [0, n_scatter) scatter chunk k, the next n_stats CTAs reduce chunk k-1, then chunk k-2 is normalised and
+// chunk k+1 zero-filled.  The stages bind on different units -- the scatter on the L2's atomic ALUs (~105 G RED/s,
+// profiles/r02/atomics_l2_probe.txt), the other three on L2 bandwidth -- and run back to back each of them left the
+// machine half idle plus a launch ramp and tail per kernel (4 launches per chunk).  B + 3 launches of this kernel
+// replace 4 B of the single-stage kernels; all chunks in flight stay L2-resident (the host sizes them).
+struct PipeStage {
+    int b0, nbat, ctas;   // windows [b0, b0 + nbat) of the batch, CTAs of this stage (0: idle)
+};
+__global__ void __launch_bounds__(kScatterThreads)
+voxel_pipeline_kernel(const double *__restrict__ ev, const int64_t *__restrict__ off, int B, int nb, int H, int W, int flavour,
+                      float *__restrict__ out, int64_t cells, int64_t chunk_len, int chunks, float hot_thr, int mode,
+                      Partial *__restrict__ partials, PipeStage scat, PipeStage stat, PipeStage norm, PipeStage zero) {
+    static_assert(kScatterThreads == kStatThreads, "one block size for all stages");
+    int blk = (int)blockIdx.x;
+    if (blk < scat.ctas) {
+        scatter_body(ev, off, B, nb, H, W, flavour, out, scat.b0, scat.b0 + scat.nbat, blk, scat.ctas);
+        return;
+    }
+    blk -= scat.ctas;
+    if (blk < stat.ctas) {
+        stats_body(out, cells, chunk_len, hot_thr, partials, chunks, stat.b0 + blk / chunks, blk % chunks);
+        return;
+    }
+    blk -= stat.ctas;
+    if (blk < norm.ctas) {
+        normalise_body(out, out, cells, chunk_len, hot_thr, mode, partials, chunks, norm.b0 + blk / chunks, blk % chunks);
+        return;
+    }
+    blk -= norm.ctas;
+    {
+        float4 *z = reinterpret_cast<float4 *>(out + (int64_t)zero.b0 * cells);   // cells % 4 == 0 (checked by the host)
+        const int64_t n4 = (int64_t)zero.nbat * cells / 4;
+        for (int64_t i = (int64_t)blk * kScatterThreads + threadIdx.x; i < n4; i += (int64_t)zero.ctas * kScatterThreads)
+            z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 static void stat_geometry(int B, int64_t cells, int &chunks, int64_t &chunk_len) {
     // ~8 CTAs per SM over the batch, chunks of >= 2048 cells (2 float4 per thread), <= kMaxChunks per window
     int64_t want = ceil_div(8 * 148, B > 0 ? B : 1);
@@ -732,8 +786,8 @@ static bool use_tiled(int64_t, int, int64_t) {
     return (voxel_flags() & 8) != 0;              // experiments: CF_VOXEL_FLAGS=8 forces the tiled path
 }
 
-// CF_VOXEL_FLAGS (debug / experiments): bit3 = force the tiled path, bit2 = force the L2-atomic path, bit1 = use the cluster / DSMEM-atomics
-// path, bit0 = do not chunk
+// CF_VOXEL_FLAGS (debug / experiments): bit4 = pipelined launches (four stages of four chunks per launch), bit3 = force the tiled path,
+// bit2 = force the L2-atomic path, bit1 = use the cluster / DSMEM-atomics path, bit0 = do not chunk
 static int voxel_flags() {
     static int flags = -1;
     if (flags < 0) {
@@ -896,6 +950,51 @@ extern "C" int cf_voxel_bin(const double *events, const int64_t *offsets, int64_
             CF_REQUIRE(ws && ws_bytes >= (size_t)B * kMaxChunks * sizeof(Partial), CF_ERR_WORKSPACE,
                        "cf_voxel_bin: workspace too small (%zu < %zu)", ws_bytes, (size_t)B * kMaxChunks * sizeof(Partial));
             CF_REQUIRE(aligned16(ws), CF_ERR_ALIGN, "cf_voxel_bin: workspace not 16-byte aligned");
+        }
+        if ((voxel_flags() & 16) && (cells & 3) == 0 && total > 0 && aligned16(out)) {
+            // ---- pipelined (experiment, CF_VOXEL_FLAGS bit4; measured SLOWER than one stage per launch on the B200: 64 x 480x640
+            //      573 against 365 us, 8 x 480x640 78 against 43 us -- the stages do not overlap usefully inside one launch):
+            //      stage s of chunk k runs in launch k + s (voxel_pipeline_kernel).  Four chunks are in
+            //      flight (zeroed | being scattered into | being reduced | being normalised): size them so that all
+            //      four stay L2-resident
+            int pc = (voxel_flags() & 1) ? B : (int)((budget_mb << 20) / (4 * per_window));
+            if (pc < 1) pc = 1;
+            if (pc > B) pc = B;
+            const int nch = (int)ceil_div(B, pc);
+            int chunks = 1;
+            int64_t chunk_len = cells;
+            if (preprocess != CF_PRE_NONE) stat_geometry(pc, cells, chunks, chunk_len);
+            Partial *partials = reinterpret_cast<Partial *>(ws);
+            const int64_t cap = (int64_t)sm_count() * 8;
+            auto stage = [&](int k, bool on) {
+                PipeStage st{0, 0, 0};
+                if (on && k >= 0 && k < nch) {
+                    st.b0 = k * pc;
+                    st.nbat = B - st.b0 < pc ? B - st.b0 : pc;
+                }
+                return st;
+            };
+            for (int step = 0; step < nch + 3; ++step) {
+                PipeStage zero = stage(step, true), scat = stage(step - 1, true);
+                PipeStage stat = stage(step - 2, preprocess != CF_PRE_NONE), norm = stage(step - 3, preprocess != CF_PRE_NONE);
+                if (zero.nbat) {
+                    int64_t c = ceil_div((int64_t)zero.nbat * cells / 4, kScatterThreads * 8);
+                    zero.ctas = (int)(c > 2 * cap ? 2 * cap : (c < 1 ? 1 : c));
+                }
+                if (scat.nbat) {
+                    int64_t blocks = ceil_div(ceil_div(total * scat.nbat, B), kScatterThreads * kScatterUnroll);
+                    scat.ctas = (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+                }
+                if (stat.nbat) stat.ctas = stat.nbat * chunks;
+                if (norm.nbat) norm.ctas = norm.nbat * chunks;
+                const int grid = zero.ctas + scat.ctas + stat.ctas + norm.ctas;
+                if (grid == 0) continue;
+                voxel_pipeline_kernel<<<(unsigned)grid, kScatterThreads, 0, stream>>>(
+                    events, offsets, B, nb, H, W, flavour, out, cells, chunk_len, chunks, hot_thr, preprocess, partials, scat, stat,
+                    norm, zero);
+                CF_LAUNCH_CHECK("voxel_pipeline_kernel");
+            }
+            return CF_OK;
         }
         for (int b0 = 0; b0 < B; b0 += chunk) {
             const int nbat = B - b0 < chunk ? B - b0 : chunk;

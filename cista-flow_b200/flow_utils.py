@@ -149,8 +149,9 @@ def warp_frame_and_codes_upflow8(img: torch.Tensor, codes: torch.Tensor, flow_lr
     if pad is None:
         pad = (8 * lh - H, 8 * lw - W)
     pad_h, pad_w = int(pad[0]), int(pad[1])
-    assert flow_lr.shape[:2] == (B, 2) and 8 * lh - pad_h == H and 8 * lw - pad_w == W, \
-        "flow_lr must be [B,2,(H+pad_h)/8,(W+pad_w)/8]"
+    if not (tuple(flow_lr.shape[:2]) == (B, 2) and 8 * lh - pad_h == H and 8 * lw - pad_w == W):
+        raise ValueError(f"flow_lr must be [B,2,(H+pad_h)/8,(W+pad_w)/8]: got {tuple(flow_lr.shape)} for a {H}x{W} frame "
+                         f"with padding ({pad_h}, {pad_w})")
     assert codes.shape[0] == B and codes.shape[2] == H // 2 and codes.shape[3] == W // 2, "codes must be [B,C,H//2,W//2]"
     img_out, codes_out = torch.empty_like(img), torch.empty_like(codes)
     flow_out = torch.empty((B, 2, H, W), dtype=torch.float32, device=img.device) if return_flow else None

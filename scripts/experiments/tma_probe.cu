@@ -129,7 +129,8 @@ static void run(const char *name, CUtensorMapDataType dt, CUtensorMapSwizzle sw,
     Cfg c{mode3d, boxes, box_cols, box_rows, elt, stages, 2000, N, rows_total};
     const int stage_bytes = boxes * box_cols * box_rows * elt;
     const int smem = stages * stage_bytes + 1024;
-    CK(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (smem > 226 * 1024) { printf("%-14s x%d stages: does not fit\n", name, stages); return; }
+    CK(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     unsigned long long *cyc;
     CK(cudaMalloc(&cyc, 148 * 8));
     for (int ctas : {1, 148}) {
