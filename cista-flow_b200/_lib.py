@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("CISTAFLOW_LIB", os.path.join(_HERE, "libcistaflow.so"
 VOXEL_ATOMIC, VOXEL_DETERMINISTIC, VOXEL_ATOMIC_L2, VOXEL_ATOMIC_TILED = 0, 1, 2, 3
 FLAVOUR_TORCH, FLAVOUR_NUMPY, FLAVOUR_POL, FLAVOUR_MVSEC = 0, 1, 2, 3
 PRE_NONE, PRE_STD, PRE_MAXMIN = 0, 1, 2
+WINDOWS_FIXED, WINDOWS_SPLIT = 0, 1
 CORR_TF32, CORR_FP32, CORR_3XTF32, CORR_F16, CORR_AUTO = 0, 1, 2, 3, 4
 CORR_MAX_LEVELS = 6
 
@@ -38,6 +39,9 @@ SYMBOLS = {
     "cf_preprocess_workspace_bytes": (_sz, [_i, _i64]),
     "cf_voxel_preprocess": (_i, [_vp, _vp, _i, _i64, _i, _f, _vp, _sz, _vp]),
     "cf_events_pack": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "cf_events_filter_workspace_bytes": (_sz, [_i64]),
+    "cf_events_filter": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "cf_event_window_offsets": (_i, [_vp, _i, _i64, _vp, _i, _vp, _vp]),
     "cf_voxel_bin_packed": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp, _vp, _sz, _vp]),
     "cf_warp": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "cf_warp_frame_and_codes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),

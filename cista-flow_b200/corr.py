@@ -19,9 +19,11 @@ from . import _lib
 
 # 'tf32' (tcgen05 tensor cores, default), 'fp32' (SIMT, the reference's arithmetic)
 # "f16" = fp16 operand copies (kind::f16): same operand significands as "tf32", measured no faster
-DEFAULT_PRECISION = os.environ.get("CISTAFLOW_CORR_PRECISION", "tf32")
-_PREC = {"tf32": _lib.CORR_TF32, "fp32": _lib.CORR_FP32, "3xtf32": _lib.CORR_3XTF32, "f16": _lib.CORR_F16,
-         "auto": _lib.CORR_AUTO}
+# "auto" (default): tensor cores, operands carrying an 11-bit significand either way -- TF32 words rounded by the TMA, or
+# fp16 copies scaled per batch item where that measured faster (wide maps); the two agree to fp32 summation-order noise
+# and the end-to-end PSNR gate (tests/test_e2e_psnr.py) is taken with exactly this operand rounding.
+DEFAULT_PRECISION = os.environ.get("CISTAFLOW_CORR_PRECISION", "auto")
+_PREC = {"tf32": _lib.CORR_TF32, "fp32": _lib.CORR_FP32, "f16": _lib.CORR_F16, "auto": _lib.CORR_AUTO}
 
 
 def coords_grid(batch, ht, wd, device=None):
@@ -164,8 +166,12 @@ class CorrBlock:
 
     @staticmethod
     def corr(fmap1, fmap2, precision=None):
-        """[B, h, w, 1, h, w] = <fmap1, fmap2> / sqrt(D)  (ERAFT/corr.py:52-60)."""
+        """[B, h, w, 1, h, w] = <fmap1, fmap2> / sqrt(D)  (ERAFT/corr.py:52-60).  Differentiable like the reference's
+        when gradients are being recorded."""
         B, D, h, w = fmap1.shape
-        with torch.no_grad():
-            vol = build_pyramid(fmap1, fmap2, 1, precision)[0]
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            vol = _PyramidFunction.apply(_prep(fmap1, "fmap1"), _prep(fmap2, "fmap2"), 1, precision)[0]
+        else:
+            with torch.no_grad():
+                vol = build_pyramid(fmap1, fmap2, 1, precision)[0]
         return vol.view(B, h, w, 1, h, w)

@@ -57,8 +57,9 @@ constexpr int BK = 32;           // K rows per pipeline stage (4 MMAs of K=8)
 // 320 ns WHATEVER its size between 20 and 40 KB (profiles/r02/tma_probe.txt: {64 cols, 32 rows, 5 atoms} and
 // {64, 64, 5} both 320 ns), and a stage is two instructions (fmap1 box + fmap2 box): with 32-row stages the fp16
 // kernel spent 8 x 2 x 320 ns = 5.1 us per tile on operand loads alone -- exactly what it measured, and why halving
-// the operand bytes had bought nothing in round 1.  Four 64-row stages are 2.6 us.
-constexpr int BK_F16 = 64;
+// the operand bytes had bought nothing in round 1.  64-row stages: 3.0 us of loads per tile (ablation: loads only), 305 us at
+// 8 x 60x80; 128-row stages (two per tile, 80 KB each, ring of two): loads + MMAs 2.45 us per tile, 290 us.
+constexpr int BK_F16 = 128;
 constexpr int MAX_STAGES = 8;     // ring depth = as many stages of (fmap1 tile + this shape's fmap2 tile) as fit, at most 6
 constexpr int MAX_BN = 256;      // UMMA N limit
 constexpr int BOX_BYTES = 32 * 32 * 4;                 // one TMA box: 32 cols x 32 rows fp32
@@ -993,7 +994,12 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // AUTO resolves to TF32: the fp16-operand variant halves the MMA time and the operand bytes and agrees with
     // TF32 to summation-order noise (same 11-bit operand significands), but measured NO faster on the B200
     // (8 x 60x80: GEMM 283 against 277 us, plus 32 us of conversion) -- the kernel is bound on the volume's write side
-    if (precision == CF_CORR_AUTO) precision = CF_CORR_TF32;
+    // AUTO (round 2): fp16 operands where they measured faster on the B200 -- wide maps whose N is a whole number of
+    // 64-column fp16 boxes and enough tiles to amortise the conversion pass (8 x 60x80: 288 against 319 us, 64 x 60x80: 2375
+    // against 2580 us) -- TF32 elsewhere (64 x 24x32: 61 against 108 us, 64 x 36x44: 336 against 374, 1 x 80x124: 183 against 205)
+    if (precision == CF_CORR_AUTO)
+        precision = (N % 64 == 0 && N >= 2048 && (int64_t)B * N >= 19200 && D % BK_F16 == 0 && ws != nullptr &&
+                     ws_bytes >= corr_tc_workspace_bytes(B, D, h, w)) ? CF_CORR_F16 : CF_CORR_TF32;
     if (precision == CF_CORR_F16 && D % BK_F16 != 0) precision = CF_CORR_TF32;   // the fp16 stages hold 64 K rows
     const bool f16 = precision == CF_CORR_F16;
     const int BC = f16 ? 64 : 32;   // operand columns per TMA box
@@ -1087,7 +1093,7 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // round 2: with 64-row fp16 stages the operand loads take 4 x 0.45 us and the MMAs 1.9 us per 128x160 tile; the
     // epilogue on four warps (3.6 us per tile, corr_trace) became the critical path -> two warps per lane quarter by
     // default for fp16 operands (flags bit7 now forces one)
-    const int es = (f16 && p.deep == 0 && !(flags & 128) && (SMEM_LIMIT - smem_fixed(2)) / p.stage_bytes >= 3) ? 2 : 1;
+    const int es = (f16 && p.deep == 0 && !(flags & 128) && (SMEM_LIMIT - smem_fixed(2)) / p.stage_bytes >= 2) ? 2 : 1;
     p.stages = (SMEM_LIMIT - smem_fixed(es)) / p.stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     // pairs of query tiles as one 256-row UMMA across two CTAs: measured slower than one CTA per tile on the B200
@@ -1097,6 +1103,11 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // level-0 rows through the LSU instead of TMA bulk stores: helps where the operand loads already need many TMA
     // instructions per stage (N % 32 != 0: 64 x 36x44 398 -> 367 us), costs 2-5 % elsewhere (flags bit0: always TMA)
     p.lsu_stores = (!(flags & 1) && !p.atoms3d && N % 4 == 0) ? 1 : 0;
+    // round 2, measured and NOT adopted for fp16 operands: (a) level-0 rows through the LSU (flags bit5): 64 x 60x80 2617
+    // against 2515 us; (b) one bulk store per 32-column chunk for all 128 rows of the tile (box {32, 128}, the four
+    // epilogue warps of a lane-quarter group meeting at a named barrier; 5 store instructions per tile instead of 20):
+    // 2704 against 2375 us (TF32: 2744 against 2580) -- the stores' instruction count is not what holds the epilogue up
+    if (f16 && N % 4 == 0 && (flags & 32)) p.lsu_stores = 1;
     // round 2: one SM's TMA unit moves about one 128-byte box row per ns, loads and stores alike (profiles/r02/tma_probe.txt),
     // and a 128x160 tile is 1280 operand rows + 640 level-0 rows: with fp16 operands the unit, not the tensor pipe or the
     // HBM, was suspected to set the tile period.  Measured (flags bit5 routes the fp16 kernel's level-0 rows through the LSU):

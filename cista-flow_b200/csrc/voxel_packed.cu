@@ -147,3 +147,186 @@ extern "C" int cf_voxel_bin_packed(const void *packed, const int64_t *offsets, i
     if (preprocess != CF_PRE_NONE) return run_preprocess_shared(out, out, B, cells, preprocess, hot_thr, ws, ws_bytes, stream);
     return CF_OK;
 }
+
+namespace cf {
+
+// ---------------------------------------------------------------- device-side windowing ---
+// What the reference's readers do on the host with pandas / NumPy before every frame
+// (data_readers/video_readers.py:208-232, data_readers/event_readers.py:6-47), on the device:
+//   cf_events_filter      keeps the rows with x < width and y < height (video_readers.py:208-209, in this order, no lower
+//                         bound -- like the reference), STABLE, compacted into `out`; the kept count goes to a device
+//                         int64 so that nothing is read back;
+//   cf_event_window_offsets   offsets[0..n] of the frame's windows from a DEVICE-resident event count:
+//                         CF_WINDOWS_FIXED  non-overlapping windows of `param` events, the last one keeps the remainder
+//                                           (FixedSizeEventReader with k_shift <= 0: pandas get_chunk)
+//                         CF_WINDOWS_SPLIT  np.array_split(events, max(1, round(n / param))): n // k + 1 events in the first
+//                                           n % k windows, n // k in the others (limit_num_events > 0, video_readers.py:219-224)
+//                         offsets beyond the last window are filled with n, so a fixed-size offsets array (max_windows + 1)
+//                         feeds cf_voxel_bin with B = max_windows and empty trailing windows -- graph-capturable.
+namespace vw {
+constexpr int THREADS = 256;
+constexpr int ITEMS = 8;                      // rows per thread
+constexpr int TILE = THREADS * ITEMS;         // 2048 rows per CTA
+
+__device__ __forceinline__ bool keep_row(const double *__restrict__ ev, int64_t i, double W, double H) {
+    const double x = __ldg(ev + 4 * i + 1), y = __ldg(ev + 4 * i + 2);
+    return x < W && y < H;
+}
+
+// kept rows per CTA tile -> counts[blockIdx.x]
+__global__ void __launch_bounds__(THREADS) filter_count_kernel(const double *__restrict__ ev, int64_t total, double W, double H,
+                                                               uint32_t *__restrict__ counts) {
+    const int64_t base = (int64_t)blockIdx.x * TILE + (int64_t)threadIdx.x * ITEMS;
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k)
+        if (base + k < total && keep_row(ev, base + k, W, H)) ++n;
+    n = warp_sum(n);
+    __shared__ int sh[THREADS / 32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < THREADS / 32; ++k) t += sh[k];
+        counts[blockIdx.x] = (uint32_t)t;
+    }
+}
+
+// exclusive scan of `n` CTA counts in place (single CTA of 1024 threads); total -> *kept
+__global__ void __launch_bounds__(1024) filter_scan_kernel(uint32_t *__restrict__ data, int64_t n, int64_t *__restrict__ kept) {
+    __shared__ uint32_t warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t per = (n + 1023) / 1024;
+    const int64_t s = (int64_t)tid * per, e = min(n, s + per);
+    uint32_t sum = 0;
+    for (int64_t i = s; i < e; ++i) sum += data[i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t t = warp_tot[lane], ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += v;
+        }
+        warp_tot[lane] = ti - t;
+        if (lane == 31) *kept = (int64_t)ti;
+    }
+    __syncthreads();
+    uint32_t run = warp_tot[warp] + inc - sum;
+    for (int64_t i = s; i < e; ++i) {
+        const uint32_t v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
+// stable scatter: thread-local ranks + warp scan + warp totals, on top of the scanned CTA base
+__global__ void __launch_bounds__(THREADS) filter_scatter_kernel(const double *__restrict__ ev, int64_t total, double W, double H,
+                                                                 const uint32_t *__restrict__ bases, double *__restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * TILE + (int64_t)threadIdx.x * ITEMS;
+    bool keep[ITEMS];
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        keep[k] = base + k < total && keep_row(ev, base + k, W, H);
+        n += keep[k];
+    }
+    int inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    __shared__ int sh[THREADS / 32];
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    int before = inc - n;
+    for (int k = 0; k < warp; ++k) before += sh[k];
+    int64_t dst = (int64_t)bases[blockIdx.x] + before;
+    const double2 *src2 = reinterpret_cast<const double2 *>(ev);
+    double2 *out2 = reinterpret_cast<double2 *>(out);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (keep[k]) {
+            out2[2 * dst] = __ldg(src2 + 2 * (base + k));
+            out2[2 * dst + 1] = __ldg(src2 + 2 * (base + k) + 1);
+            ++dst;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) window_offsets_kernel(const int64_t *__restrict__ count, int policy, int64_t param,
+                                                             int64_t *__restrict__ offsets, int max_windows, int *__restrict__ n_windows) {
+    const int64_t n = *count;
+    int64_t k;      // number of windows
+    if (policy == CF_WINDOWS_FIXED) {
+        k = (n + param - 1) / param;
+    } else {
+        // Python round(): half to even, on the fp64 quotient (video_readers.py:220)
+        k = (int64_t)rint((double)n / (double)param);
+        if (k == 0) k = 1;
+    }
+    if (k > max_windows) k = max_windows;    // (the caller sized the array; the last window then keeps the rest)
+    const int64_t q = k > 0 ? n / k : 0, r = k > 0 ? n % k : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= max_windows; i += gridDim.x * blockDim.x) {
+        int64_t o;
+        if (i >= k) o = n;
+        else if (policy == CF_WINDOWS_FIXED) o = (int64_t)i * param < n ? (int64_t)i * param : n;
+        else o = (int64_t)i * q + (i < r ? i : r);          // np.array_split: the first n % k sections get one more
+        offsets[i] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_windows) *n_windows = (int)k;
+}
+}  // namespace vw
+}  // namespace cf
+
+extern "C" size_t cf_events_filter_workspace_bytes(int64_t total_events) {
+    const int64_t tiles = ((total_events > 0 ? total_events : 1) + cf::vw::TILE - 1) / cf::vw::TILE;
+    return cf::align_up((size_t)tiles * sizeof(uint32_t), 256);
+}
+
+extern "C" int cf_events_filter(const double *events, int64_t total, int W, int H, double *out, int64_t *kept,
+                                void *ws, size_t ws_bytes, cf_stream_t stream_) {
+    using namespace cf;
+    if (int rc = check_device()) return rc;
+    CF_REQUIRE(kept && (total == 0 || (events && out)), CF_ERR_NULL, "cf_events_filter: null pointer");
+    CF_REQUIRE(total >= 0 && W > 0 && H > 0, CF_ERR_INVALID_ARG, "cf_events_filter: bad size");
+    CF_REQUIRE(total < (1ll << 32), CF_ERR_INVALID_ARG, "cf_events_filter: more than 2^32 events in one call");
+    CF_REQUIRE(total == 0 || (aligned16(events) && aligned16(out)), CF_ERR_ALIGN, "cf_events_filter: events not 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (total == 0) {
+        CF_CUDA(cudaMemsetAsync(kept, 0, sizeof(int64_t), stream));
+        return CF_OK;
+    }
+    const int64_t tiles = ceil_div(total, vw::TILE);
+    CF_REQUIRE(ws && ws_bytes >= (size_t)tiles * sizeof(uint32_t), CF_ERR_WORKSPACE, "cf_events_filter: workspace too small");
+    uint32_t *counts = reinterpret_cast<uint32_t *>(ws);
+    vw::filter_count_kernel<<<(unsigned)tiles, vw::THREADS, 0, stream>>>(events, total, (double)W, (double)H, counts);
+    CF_LAUNCH_CHECK("filter_count_kernel");
+    vw::filter_scan_kernel<<<1, 1024, 0, stream>>>(counts, tiles, kept);
+    CF_LAUNCH_CHECK("filter_scan_kernel");
+    vw::filter_scatter_kernel<<<(unsigned)tiles, vw::THREADS, 0, stream>>>(events, total, (double)W, (double)H, counts, out);
+    CF_LAUNCH_CHECK("filter_scatter_kernel");
+    return CF_OK;
+}
+
+extern "C" int cf_event_window_offsets(const int64_t *count, int policy, int64_t param, int64_t *offsets, int max_windows,
+                                       int *n_windows, cf_stream_t stream_) {
+    using namespace cf;
+    if (int rc = check_device()) return rc;
+    CF_REQUIRE(count && offsets, CF_ERR_NULL, "cf_event_window_offsets: null pointer");
+    CF_REQUIRE(policy == CF_WINDOWS_FIXED || policy == CF_WINDOWS_SPLIT, CF_ERR_INVALID_ARG, "cf_event_window_offsets: bad policy %d", policy);
+    CF_REQUIRE(param > 0 && max_windows > 0, CF_ERR_INVALID_ARG, "cf_event_window_offsets: param and max_windows must be > 0");
+    vw::window_offsets_kernel<<<(unsigned)ceil_div(max_windows + 1, 256), 256, 0, (cudaStream_t)stream_>>>(count, policy, param, offsets,
+                                                                                                    max_windows, n_windows);
+    CF_LAUNCH_CHECK("window_offsets_kernel");
+    return CF_OK;
+}

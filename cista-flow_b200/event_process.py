@@ -181,6 +181,45 @@ def events_to_voxel_grid_packed(packed: torch.Tensor, offsets: torch.Tensor, num
     return out
 
 
+# ---- device-side windowing (include/cistaflow.h: cf_events_filter, cf_event_window_offsets) -----------------------------
+def filter_events(events: torch.Tensor, width: int, height: int):
+    """``event_window[event_window[:,1] < width]`` then ``[:,2] < height`` (data_readers/video_readers.py:208-209) on the
+    device, stable, without a read-back: returns (compacted float64 [N,4] buffer, device int64 scalar = rows kept).
+    Rows past the kept count are unspecified."""
+    _lib.require_cuda(events, "events")
+    assert events.dim() == 2 and events.shape[1] == 4
+    events = events.double().contiguous()
+    n = events.shape[0]
+    out = torch.empty_like(events)
+    kept = torch.empty(1, dtype=torch.int64, device=events.device)
+    lib = _lib.load()
+    with torch.cuda.device(events.device):
+        ws_bytes = lib.cf_events_filter_workspace_bytes(n)
+        ws = _lib.workspace(ws_bytes, events.device)
+        rc = lib.cf_events_filter(_lib.ptr(events) if n else None, n, int(width), int(height), _lib.ptr(out) if n else None,
+                                  kept.data_ptr(), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(events.device))
+    _lib.check(rc, "cf_events_filter")
+    return out, kept
+
+
+def window_offsets(count: torch.Tensor, param: int, max_windows: int, policy: str = "fixed"):
+    """Window boundaries from a device-resident event count: policy 'fixed' = windows of ``param`` events, the last keeps
+    the remainder (FixedSizeEventReader, data_readers/event_readers.py:6-47); 'split' = ``np.array_split`` into
+    ``max(1, round(count / param))`` windows (limit_num_events, video_readers.py:219-224).  Returns (offsets int64
+    [max_windows + 1] with trailing empty windows, device int32 scalar = number of windows) -- both stay on the device."""
+    _lib.require_cuda(count, "count")
+    assert count.dtype == torch.int64 and count.numel() == 1
+    offsets = torch.empty(max_windows + 1, dtype=torch.int64, device=count.device)
+    n_windows = torch.empty(1, dtype=torch.int32, device=count.device)
+    pol = {"fixed": _lib.WINDOWS_FIXED, "split": _lib.WINDOWS_SPLIT}[policy]
+    lib = _lib.load()
+    with torch.cuda.device(count.device):
+        rc = lib.cf_event_window_offsets(count.data_ptr(), pol, int(param), offsets.data_ptr(), int(max_windows),
+                                         n_windows.data_ptr(), _lib.stream_ptr(count.device))
+    _lib.check(rc, "cf_event_window_offsets")
+    return offsets, n_windows
+
+
 def _single_window(events_dev: torch.Tensor, num_bins, width, height, flavour, mode, **kw) -> torch.Tensor:
     n = events_dev.shape[0]
     offsets = torch.tensor([0, n], dtype=torch.int64, device=events_dev.device)

@@ -31,6 +31,20 @@ def _as_tensor(a):
     return torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
 
 
+def _binary_search(t, l, r, x):
+    """binary_search_torch_tensor (MVSEC_utils.py:184-201, side='left') on a host tensor."""
+    while l <= r:
+        mid = l + (r - l) // 2
+        midval = t[mid]
+        if midval == x:
+            return mid
+        if midval < x:
+            l = mid + 1
+        else:
+            r = mid - 1
+    return l
+
+
 def _voxel(xs, ys, ts, weights, B, sensor_size, mode):
     """[B,H,W] float32 on the current CUDA device from per-event columns (any device, any real dtype)."""
     dev = event_process._device()
@@ -48,9 +62,22 @@ def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)
     """MVSEC_utils.py:253-303 (temporal bilinear): voxel[b, y, x] = sum_e ps_e * max(0, 1 - |t*_e - b|)."""
     xs, ys, ts, ps = (_as_tensor(a) for a in (xs, ys, ts, ps))
     assert len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps)
-    if not temporal_bilinear:
-        raise NotImplementedError("temporal_bilinear=False is not mirrored (unused by the reference's callers)")
     where = torch.device(device) if device is not None else xs.device
+    if not temporal_bilinear:
+        # MVSEC_utils.py:292-300: bin bi takes the events with ts in [ts[0] + dt*bi, ts[0] + dt*(bi+1)), dt the WHOLE
+        # window (sic), their polarities accumulated per pixel.  The index range comes from the reference's own binary
+        # search (host side, on the time column); each bin is one single-bin voxelisation on the GPU.
+        n = len(ts)
+        if n == 0:
+            return torch.zeros((int(B), int(sensor_size[0]), int(sensor_size[1])), dtype=torch.float32, device=where)
+        tc = ts.detach().cpu()
+        dt = tc[-1] - tc[0]
+        bins = []
+        for bi in range(int(B)):
+            tstart = tc[0] + dt * bi
+            beg, end = _binary_search(tc, 0, n - 1, tstart), _binary_search(tc, 0, n - 1, tstart + dt)
+            bins.append(_voxel(xs[beg:end], ys[beg:end], ts[beg:end], ps[beg:end], 1, sensor_size, mode)[0])
+        return torch.stack(bins).to(where)
     return _voxel(xs, ys, ts, ps, int(B), sensor_size, mode).to(where)
 
 

@@ -135,6 +135,21 @@ CF_API int cf_voxel_preprocess(const float *in, float *out, int B, int64_t cells
 /* events float64 [total,4] + offsets int64 [B+1] (as cf_voxel_bin) -> packed uint64 [total]. */
 CF_API int cf_events_pack(const double *events, const int64_t *offsets, int64_t total_events, int B,
                    void *packed, cf_stream_t stream);
+/* Device-side windowing (what data_readers/video_readers.py:208-232 and data_readers/event_readers.py:6-47 do on the host
+ * before every frame), so that a raw event stream uploaded once is cut into voxel windows without a read-back:
+ *   cf_events_filter   rows with x < W and y < H (video_readers.py:208-209; no lower bound, like the reference), stable,
+ *                      compacted into out [<= total,4]; *kept (device int64) = rows kept.
+ *                      workspace: cf_events_filter_workspace_bytes(total).
+ *   cf_event_window_offsets   offsets [max_windows+1] from a DEVICE-resident count:
+ *                      CF_WINDOWS_FIXED  windows of `param` events, the last keeps the remainder (FixedSizeEventReader)
+ *                      CF_WINDOWS_SPLIT  np.array_split into max(1, round(count / param)) windows (limit_num_events)
+ *                      entries past the last window = count (empty windows); *n_windows (device int, may be NULL). */
+enum cf_window_policy { CF_WINDOWS_FIXED = 0, CF_WINDOWS_SPLIT = 1 };
+CF_API size_t cf_events_filter_workspace_bytes(int64_t total_events);
+CF_API int cf_events_filter(const double *events, int64_t total_events, int W, int H, double *out, int64_t *kept,
+                     void *workspace, size_t workspace_bytes, cf_stream_t stream);
+CF_API int cf_event_window_offsets(const int64_t *count, int policy, int64_t param, int64_t *offsets, int max_windows,
+                            int *n_windows, cf_stream_t stream);
 /* Voxel grid [B, nb, H, W] (+ fused event_preprocess) from packed events; ATOMIC numerics
  * (|err| <= 1e-5 * (sum|w| + 1) per cell against the fp64 reference), polarity 0 -> -1 like
  * events_to_voxel_grid.  workspace: cf_preprocess_workspace_bytes(B, nb*H*W) when preprocess != NONE. */
@@ -231,7 +246,7 @@ typedef enum cf_corr_precision {
                            operand, scaled per batch item by a power of two so that every finite input fits; K = 16
                            per MMA and half the operand bytes.  Within fp32 summation-order noise of TF32; measured no
                            faster on a B200 (the kernel is bound on the volume's write side), kept as an option */
-    CF_CORR_AUTO = 4    /* the library's choice (currently TF32) */
+    CF_CORR_AUTO = 4    /* the library's choice by shape: fp16 operand copies for wide maps (N % 64 == 0, many tiles), else TF32 */
 } cf_corr_precision;
 
 #define CF_CORR_MAX_LEVELS 6

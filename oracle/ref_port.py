@@ -141,6 +141,36 @@ def mvsec_voxel_torch(xs, ys, ts, ps, num_bins: int, height: int, width: int) ->
     return grid
 
 
+def mvsec_binary_search(t: torch.Tensor, l: int, r: int, x) -> int:
+    """``binary_search_torch_tensor`` (MVSEC_utils.py:184-201), side='left'."""
+    while l <= r:
+        mid = l + (r - l) // 2
+        midval = t[mid]
+        if midval == x:
+            return mid
+        if midval < x:
+            l = mid + 1
+        else:
+            r = mid - 1
+    return l
+
+
+def mvsec_voxel_naive_torch(xs, ys, ts, ps, num_bins: int, height: int, width: int) -> torch.Tensor:
+    """``events_to_voxel_torch(..., temporal_bilinear=False)`` (MVSEC_utils.py:292-300): bin bi accumulates the polarities of
+    the events with ts in [ts[0] + dt*bi, ts[0] + dt*(bi+1)), dt = ts[-1] - ts[0] (the whole window, as written there)."""
+    xs, ys, ts, ps = (torch.as_tensor(a) for a in (xs, ys, ts, ps))
+    with torch.no_grad():
+        grid = torch.zeros((num_bins, height, width), dtype=torch.float32)
+        dt = ts[-1] - ts[0]
+        for b in range(num_bins):
+            tstart = ts[0] + dt * b
+            tend = tstart + dt
+            beg = mvsec_binary_search(ts, 0, len(ts) - 1, tstart)
+            end = mvsec_binary_search(ts, 0, len(ts) - 1, tend)
+            grid[b].index_put_((ys[beg:end].long(), xs[beg:end].long()), ps[beg:end].float(), accumulate=True)
+    return grid
+
+
 def mvsec_events_to_voxel(events_xytp: np.ndarray, num_bins: int, height: int, width: int,
                           event_polarity: bool = False) -> np.ndarray:
     """``eventsToVoxel`` (MVSEC_utils.py:384-403) on rows (x, y, t, p): ``eventsToXYTP(process=True)`` (:348-364)

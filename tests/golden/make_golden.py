@@ -195,6 +195,10 @@ def make_mvsec():
         out[f"{name}/voxel_pol"] = mu.eventsToVoxel(xytp.copy(), num_bins=5, height=h, width=w, event_polarity=True)
         xs, ys, ts, ps = mu.eventsToXYTP(xytp.copy(), process=True)
         out[f"{name}/direct"] = mu.events_to_voxel_torch(xs, ys, ts, ps, 5, sensor_size=(h, w)).numpy()
+        # temporal_bilinear=False (MVSEC_utils.py:292-300): bin bi takes the events in [ts[0] + dt*bi, ts[0] + dt*(bi+1)) with
+        # dt the WHOLE window (sic), found by the reference's own binary search
+        out[f"{name}/naive"] = mu.events_to_voxel_torch(torch.from_numpy(xs), torch.from_numpy(ys), torch.from_numpy(ts),
+                                                        torch.from_numpy(ps), 5, sensor_size=(h, w), temporal_bilinear=False).numpy()
     save("mvsec.npz", **out)
 
 

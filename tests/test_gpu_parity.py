@@ -476,8 +476,9 @@ def test_mvsec_voxeliser_golden(golden, cuda_device, case):
     direct = cf.events_to_voxel_torch(xs.int(), ys.int(), (ts - ts[0]) / (ts[-1] - ts[0]), ps.int(), nb, sensor_size=(h, w),
                                       device=cuda_device, mode="deterministic")
     assert direct.device.type == "cuda" and np.array_equal(bits(direct.cpu().numpy()), bits(g[f"{case}/direct"]))
-    with pytest.raises(NotImplementedError):
-        cf.events_to_voxel_torch(xs, ys, ts, ps, nb, sensor_size=(h, w), temporal_bilinear=False)
+    naive = cf.events_to_voxel_torch(xs.int(), ys.int(), (ts - ts[0]) / (ts[-1] - ts[0]), ps.int(), nb, sensor_size=(h, w),
+                                     device=cuda_device, temporal_bilinear=False, mode="deterministic")
+    assert np.array_equal(bits(naive.cpu().numpy()), bits(g[f"{case}/naive"]))   # MVSEC_utils.py:292-300
 
 
 def test_mvsec_voxeliser_config_shape(cuda_device):

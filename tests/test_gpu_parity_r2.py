@@ -198,3 +198,39 @@ def test_upflow8_unpad_warp_vs_oracle(cuda_device, h, w, batch, channels, mode):
     with pytest.raises(ValueError):
         cf.warp_frame_and_codes_upflow8(dev_t(img, cuda_device), dev_t(codes, cuda_device), dev_t(lr, cuda_device), mode,
                                         pad=(pad[0] + 8, pad[1]))
+
+
+# ------------------------------------------------------- device-side windowing ---
+@pytest.mark.parametrize("n,limit", [(100000, 30000), (100001, 33334), (5, 30000), (0, 1000), (45000, 30000), (75000, 30000)])
+def test_device_windowing_matches_the_reference_reader(cuda_device, n, limit):
+    """video_readers.py:208-232 on the device: the x < W / y < H filter (stable compaction), np.array_split into
+    round(n / limit) windows (round-half-even), then the voxel grids of those windows -- against the same steps in NumPy
+    + the sequential oracle.  No read-back between the steps."""
+    h, w = 60, 80
+    ev = synth.events(n, h, w, seed=55) if n else np.zeros((0, 4))
+    if n:
+        rng = np.random.default_rng(2)
+        bad = rng.random(n) < 0.03                      # sensor rows the reader drops: x == W, y >= H
+        ev[bad, 1] = np.where(rng.random(bad.sum()) < 0.5, w, ev[bad, 1])
+        ev[bad, 2] = np.where(ev[bad, 1] < w, h + 1, ev[bad, 2])
+    ref = ev[ev[:, 1] < w]
+    ref = ref[ref[:, 2] < h]
+    k = round(ref.shape[0] / limit) or 1
+    parts = np.array_split(ref, k, axis=0)
+    out, kept = cf.filter_events(dev_t(ev, cuda_device), w, h)
+    max_windows = 8
+    offs, n_win = cf.window_offsets(kept, limit, max_windows, policy="split")
+    assert kept.item() == ref.shape[0] and n_win.item() == min(k, max_windows)
+    assert np.array_equal(out[: ref.shape[0]].cpu().numpy(), ref)
+    sizes = np.diff(offs.cpu().numpy())
+    assert list(sizes[:k]) == [len(p) for p in parts] and (sizes[k:] == 0).all()
+    grids = cf.events_to_voxel_grid_batched(out, offs, 5, w, h, flavour="numpy", mode="deterministic").cpu().numpy()
+    for i, part in enumerate(parts):
+        if len(part):
+            assert np.array_equal(bits(grids[i]), bits(explicit.voxel_grid_sequential(part, 5, w, h, explicit.FLAVOUR_NUMPY)))
+    assert not grids[k:].any()
+    # fixed-size windows (FixedSizeEventReader): the last window keeps the remainder
+    offs_f, n_f = cf.window_offsets(kept, 30000, max_windows, policy="fixed")
+    m = ref.shape[0]
+    want = [min(i * 30000, m) for i in range(max_windows + 1)]
+    assert offs_f.cpu().tolist() == want and n_f.item() == -(-m // 30000)

@@ -167,6 +167,10 @@ def test_mvsec_voxeliser_ref_port_bit_exact(golden, case):
     assert np.array_equal(got.view(np.uint32), g[f"{case}/voxel"].view(np.uint32))
     assert np.array_equal(got_pol.view(np.uint32), g[f"{case}/voxel_pol"].view(np.uint32))
     assert np.array_equal(g[f"{case}/direct"], g[f"{case}/voxel"])
+    xs_, ys_, ps_ = (torch.from_numpy(ev[:, k].astype(np.int32)) for k in (0, 1, 3))
+    ts_ = torch.from_numpy((ev[:, 2] - ev[0, 2]) / (ev[-1, 2] - ev[0, 2]))
+    naive = ref_port.mvsec_voxel_naive_torch(xs_, ys_, ts_, ps_, nb, h, w).numpy()
+    assert np.array_equal(naive, g[f"{case}/naive"])
     if case == "binary":   # 0 / 1 polarities: negative events contribute nothing (MVSEC_utils.py:355,364)
         assert (g[f"{case}/voxel"] >= 0).all()
 
