@@ -60,6 +60,8 @@ constexpr int BK = 32;           // K rows per pipeline stage (4 MMAs of K=8)
 // the operand bytes had bought nothing in round 1.  64-row stages: 3.0 us of loads per tile (ablation: loads only), 305 us at
 // 8 x 60x80; 128-row stages (two per tile, 80 KB each, ring of two): loads + MMAs 2.45 us per tile, 290 us.
 constexpr int BK_F16 = 128;
+constexpr int BK_TF32 = 32;      // TF32 stages.  64-row stages (ring of two) measured the same within 2 % at every shape (64 x 60x80 2595
+                                 // against 2580 us): the TF32 kernel is bound by its MMAs (3.0 us per 128x160 tile), not by TMA issue
 constexpr int MAX_STAGES = 8;     // ring depth = as many stages of (fmap1 tile + this shape's fmap2 tile) as fit, at most 6
 constexpr int MAX_BN = 256;      // UMMA N limit
 constexpr int BOX_BYTES = 32 * 32 * 4;                 // one TMA box: 32 cols x 32 rows fp32
@@ -103,6 +105,8 @@ struct Params {
     const float *inv_scale;  // F16 operands: [2*B] powers of two that undo the per-item operand scaling (else nullptr)
     // deep fusion (tiles of 8k whole target rows, i.e. feature maps up to 32 wide -- the 180x240 / DAVIS240 case):
     // levels 2 and 3 are pooled from the level-1 rows while they are still in registers
+    int pair2;     // 1: a CTA takes tiles in PAIRS of consecutive target-row pairs (nb, nb+1) and the epilogue pools level 2 from
+                   //    the two level-1 rows (the first one parked in free TMEM columns) -- maps too wide for `deep`, R == 2
     int deep;      // 0: none, 1: level 2, 2: levels 2 and 3
     int h2, w2, h3, w3;
     float *l2;
@@ -260,6 +264,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 16 consecutive columns, registers -> TMEM / TMEM -> registers (the level-1 row parked between two tiles)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -384,7 +406,7 @@ __device__ __forceinline__ void store_row_chunk(float *dst, const uint32_t (&v)[
 // power of two so that any finite input fits; made by fmap_to_half_kernel).  kind::f16 covers K = 16 per MMA where
 // kind::tf32 covers 8 at the same ~1 accumulator column per clock, and every stage moves half the bytes: the GEMM
 // stops being MMA / load-latency bound and runs at the HBM write rate of the volume.
-template <int CL, bool F16, int ES>
+template <int CL, bool F16, int ES, int BKT>
 __global__ void __launch_bounds__(threads(ES), 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const Params p) {
@@ -394,7 +416,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int EPI_SPLIT = ES, EPI_WARPS = 4 * ES, EPI_BYTES = epi_bytes(ES);
     constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
     constexpr int BC = F16 ? 64 : 32;                   // operand columns per TMA box (128 bytes)
-    constexpr int BKK = F16 ? BK_F16 : BK;              // K rows per stage
+    constexpr int BKK = F16 ? BK_F16 : BKT;             // K rows per stage (TF32: 64, or 32 for D % 64 != 0 and the CTA-pair kernel)
     constexpr int BOXB = 128 * BKK;                     // bytes of one TMA box: 128-byte rows x BKK
     constexpr int ABYTES = (BM / BC) * BOXB;            // fmap1 part of a stage
     constexpr int MMAS = F16 ? BKK / 16 : BKK / 8;      // MMAs per stage
@@ -410,6 +432,10 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int kblocks = p.D / BKK;
     const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
     const int first_tile = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
+    // the s-th tile of this CTA: tile indices have the target-row pair nb fastest, so with pair2 a CTA takes the two tiles
+    // 2u, 2u+1 of unit u back to back (same batch item, same query rows, target rows 4u' .. 4u'+3)
+    const int GS = p.pair2 ? 2 : 1;
+    auto tile_of = [&](int sq) { return GS * (first_tile + (sq / GS) * tile_step) + (sq % GS); };
     if (threadIdx.x == 0) stamp(0);
 
     if (warp == PRODUCER_WARP && lane == 0) {
@@ -446,7 +472,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t tx_bytes = (uint32_t)(CL * (BM / BC + (CL == 2 ? p.b_half : p.n_boxes_b))) * BOXB;
             const int jr = CL == 2 ? rank * (p.BN_mma / 2) : 0;  // first fmap2 column of this CTA inside the tile
             int tile_no = 0;
-            for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
+            for (int tile = tile_of(0); tile < p.total_tiles; tile = tile_of(++tile_no)) {
                 int b, mb, nb;
                 if (CL == 2) decode_pair_tile(p, tile, rank, b, mb, nb);
                 else decode_tile(p, tile, b, mb, nb);
@@ -501,7 +527,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     } else {
                         for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOXB, &tmap_b, j0 + BC * a, krow, &full[stage]);
                     }
-                    if (tile == first_tile && kb == 0) stamp(2);
+                    if (tile_no == 0 && kb == 0) stamp(2);
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -523,7 +549,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t lbo_bits = ((uint32_t)BOXB >> 4) << 16;   // bytes between column atoms = one TMA box
             const uint32_t smem_base = smem_u32(smem);
             int tile_no = 0;
-            for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
+            for (int tile = tile_of(0); tile < p.total_tiles; tile = tile_of(++tile_no)) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
                 tc_fence_after();
                 if (lane == 0) TC_TRACE(tile_no, 2);
@@ -532,7 +558,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     if (lane == 0) {
-                        if (tile == first_tile && kb < 16) stamp(3 + kb);
+                        if (tile_no == 0 && kb < 16) stamp(3 + kb);
                         if (kb < 8) TC_TRACE(tile_no, 3 + kb);
                     }
                     const uint32_t sa = smem_base + (uint32_t)(stage * STAGE_BYTES);
@@ -561,7 +587,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    if (tile == first_tile) stamp(19);
+                    if (tile_no == 0) stamp(19);
                     TC_TRACE(tile_no, 11);
                 }
                 acc ^= 1;
@@ -580,7 +606,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool vec4_l1 = (p.w1 % 4) == 0;
         uint8_t *my_epi = epi + warp * 2 * EPI_BUF_BYTES;
         int tile_no = 0;
-        for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tile_no) {
+        for (int tile = tile_of(0); tile < p.total_tiles; tile = tile_of(++tile_no)) {
             int b, mb, nb;
             if (CL == 2) decode_pair_tile(p, tile, rank, b, mb, nb);
             else decode_tile(p, tile, b, mb, nb);
@@ -590,7 +616,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const float scale = F16 ? p.scale * __ldg(p.inv_scale + b) * __ldg(p.inv_scale + p.B + b) : p.scale;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            if (tile == first_tile && threadIdx.x == 0) stamp(20);
+            if (tile_no == 0 && threadIdx.x == 0) stamp(20);
             if (threadIdx.x == 0) TC_TRACE(tile_no, 12);
             if (p.ablate & 16) {  // experiment: the epilogue reads nothing (MMA issue rate without TMEM read traffic)
                 tc_fence_before();
@@ -748,6 +774,37 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                     if (2 * q < npool) *(reinterpret_cast<float2 *>(dst) + q) = make_float2(o[2 * q], o[2 * q + 1]);
                             }
                         }
+                        if (p.pair2) {
+                            // level 2 across the tile pair: the first tile parks its level-1 strip in TMEM columns
+                            // [BN_mma, BN_mma + w1) of stage 0's window (free: BN_mma + w1 <= 256), the second tile pools
+                            // ATen-style ((a + b) + c) + d, / 4 and stores 8 level-2 values per query and strip
+                            const uint32_t park = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)p.BN_mma + (uint32_t)(xc >> 1);
+                            if ((nb & 1) == 0) {
+                                uint32_t ov[16];
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) ov[q] = __float_as_uint(o[q]);
+                                tmem_st16(park, ov);
+                            } else {
+                                uint32_t pv[16];
+                                tmem_ld16(park, pv);
+                                float l2v[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    float s2 = __uint_as_float(pv[2 * q]) + __uint_as_float(pv[2 * q + 1]);
+                                    s2 += o[2 * q];
+                                    s2 += o[2 * q + 1];
+                                    l2v[q] = s2 * 0.25f;
+                                }
+                                const int r2g = nb >> 1, n2 = min(8, p.w2 - (xc >> 2));
+                                if (row_ok && r2g < p.h2 && !(p.ablate & 1)) {
+                                    float *d2 = p.l2 + (((size_t)b * p.N + i) * p.h2 + r2g) * p.w2 + (xc >> 2);   // w2 % 4 == 0
+#pragma unroll
+                                    for (int q = 0; q < 2; ++q)
+                                        if (4 * q < n2)
+                                            *(reinterpret_cast<float4 *>(d2) + q) = make_float4(l2v[4 * q], l2v[4 * q + 1], l2v[4 * q + 2], l2v[4 * q + 3]);
+                                }
+                            }
+                        }
                         if (p.deep) {   // w <= 32: this is the only 32-column strip of the row pair
                             // ATen avg_pool2d again, on the level-1 (then level-2) values just stored
                             const int r1g = y >> 1;
@@ -811,7 +868,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_before();
             if (CL == 2) mbar_arrive_cluster(mapa_rank0(&tempty[acc]));
             else mbar_arrive(&tempty[acc]);
-            if (tile == first_tile && threadIdx.x == 0) stamp(21);
+            if (tile_no == 0 && threadIdx.x == 0) stamp(21);
             if (threadIdx.x == 0) TC_TRACE(tile_no, 14);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -900,6 +957,72 @@ fmap_to_half_kernel(const float *__restrict__ f1, const float *__restrict__ f2, 
     }
 }
 
+// One pass instead of two (round 2): a CTA keeps its 32 KB slice of a feature map in REGISTERS (8 float4 per thread),
+// publishes the slice's maximum (atomicMax on the item's slot + an arrival counter), waits until all slices of the item have
+// arrived, then scales and narrows out of registers -- the fp32 maps cross the HBM interface once.  The two-kernel form
+// (maximum pass, then conversion pass, chunked so that the second read hit the L2) measured 342 us for 64 x 2 maps of 256 x
+// 60x80 under ncu -- 15 % of the whole pyramid build.  Units are ordered by item and there are no more slices per item
+// than CTAs, so a CTA never waits for a slice that is queued behind its own (all CTAs of the launch fit on the chip at once).
+constexpr int CV_THREADS = 256, CV_F4 = 8;
+__global__ void __launch_bounds__(CV_THREADS)
+fmap_to_half_fused_kernel(const float *__restrict__ f1, const float *__restrict__ f2, int64_t per_item, int B, int parts,
+                          unsigned *amax, int *arrived, __half *__restrict__ h1, __half *__restrict__ h2,
+                          float *__restrict__ inv_scale) {
+    __shared__ float s_red[CV_THREADS / 32];
+    __shared__ float s_up;
+    const int64_t units = (int64_t)2 * B * parts, n4 = per_item >> 2;
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const int item = (int)(u / parts), part = (int)(u - (int64_t)item * parts);
+        const bool first = item < B;
+        const int64_t base = (int64_t)(first ? item : item - B) * per_item;
+        const float4 *s4 = reinterpret_cast<const float4 *>((first ? f1 : f2) + base);
+        uint2 *d4 = reinterpret_cast<uint2 *>((first ? h1 : h2) + base);
+        const int64_t i0 = (int64_t)part * (CV_THREADS * CV_F4) + threadIdx.x;
+        float4 v[CV_F4];
+        float m = 0.f;
+#pragma unroll
+        for (int k = 0; k < CV_F4; ++k) {
+            const int64_t i = i0 + (int64_t)k * CV_THREADS;
+            v[k] = i < n4 ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(v[k].x), fabsf(v[k].y))), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
+        }
+        m = warp_max(m);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < CV_THREADS / 32; ++k) m = fmaxf(m, s_red[k]);
+            if (m > 0.f) atomicMax(amax + item, __float_as_uint(fminf(m, 3.0e38f)));
+            __threadfence();
+            atomicAdd(arrived + item, 1);
+            unsigned spins = 0;
+            while (*reinterpret_cast<volatile int *>(arrived + item) < parts) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) __trap();
+            }
+            __threadfence();
+            const float mx = __uint_as_float(*reinterpret_cast<volatile unsigned *>(amax + item));
+            const int shift = mx > 0.f ? 13 - ilogbf(mx) : 0;
+            const float up = ldexpf(1.f, shift > 126 ? 126 : shift);      // (a tiny maximum: clamp the exponent, still exact)
+            s_up = up;
+            if (part == 0) inv_scale[item] = 1.f / up;
+        }
+        __syncthreads();
+        const float up = s_up;
+#pragma unroll
+        for (int k = 0; k < CV_F4; ++k) {
+            const int64_t i = i0 + (int64_t)k * CV_THREADS;
+            if (i < n4) {
+                const __half2 lo = __floats2half2_rn(v[k].x * up, v[k].y * up), hi = __floats2half2_rn(v[k].z * up, v[k].w * up);
+                uint2 o;
+                o.x = *reinterpret_cast<const unsigned *>(&lo);
+                o.y = *reinterpret_cast<const unsigned *>(&hi);
+                d4[i] = o;
+            }
+        }
+        __syncthreads();   // s_red / s_up are reused by the next unit
+    }
+}
+
 // ---- host side --------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -978,7 +1101,7 @@ bool corr_tensor_core_supported(int D, int h, int w) {
 // fp16 operand copies of both feature maps + per-item maxima and inverse scales (CF_CORR_F16 / CF_CORR_AUTO)
 size_t corr_tc_workspace_bytes(int B, int D, int h, int w) {
     const size_t per_map = align_up((size_t)B * D * h * w * sizeof(__half), 256);
-    return 2 * per_map + align_up((size_t)4 * B * sizeof(float), 256);
+    return 2 * per_map + align_up((size_t)6 * B * sizeof(float), 256);   // maxima, inverse scales, arrival counters
 }
 
 // flags (debug/experiments, env CF_TC_FLAGS): bit1 = encode the tensor maps as plain FLOAT32 (operands are
@@ -1000,7 +1123,7 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     if (precision == CF_CORR_AUTO)
         precision = (N % 64 == 0 && N >= 2048 && (int64_t)B * N >= 19200 && D % BK_F16 == 0 && ws != nullptr &&
                      ws_bytes >= corr_tc_workspace_bytes(B, D, h, w)) ? CF_CORR_F16 : CF_CORR_TF32;
-    if (precision == CF_CORR_F16 && D % BK_F16 != 0) precision = CF_CORR_TF32;   // the fp16 stages hold 64 K rows
+    if (precision == CF_CORR_F16 && D % BK_F16 != 0) precision = CF_CORR_TF32;   // the fp16 stages hold 128 K rows
     const bool f16 = precision == CF_CORR_F16;
     const int BC = f16 ? 64 : 32;   // operand columns per TMA box
     const void *a = f1, *bm = f2;
@@ -1015,6 +1138,20 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         __half *h1 = reinterpret_cast<__half *>(ws), *h2 = reinterpret_cast<__half *>(reinterpret_cast<char *>(ws) + per_map);
         unsigned *amax = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(ws) + 2 * per_map);
         float *inv = reinterpret_cast<float *>(amax + 2 * B);
+        int *arrived = reinterpret_cast<int *>(inv + 2 * B);
+        const int parts = (int)ceil_div(per_item / 4, CV_THREADS * CV_F4);
+        int resident = 0;
+        CF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fmap_to_half_fused_kernel, CV_THREADS, 0));
+        const int64_t cap = (int64_t)resident * sm_count();
+        if (parts <= cap && !(flags & (1 << 16))) {   // (flags bit16: the two-pass form)
+            // one pass: every slice of an item is in flight at once (parts <= CTAs of the launch)
+            CF_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned) * 2 * B, stream));
+            CF_CUDA(cudaMemsetAsync(arrived, 0, sizeof(int) * 2 * B, stream));
+            const int64_t units = (int64_t)2 * B * parts;
+            fmap_to_half_fused_kernel<<<(unsigned)(units < cap ? units : cap), CV_THREADS, 0, stream>>>(f1, f2, per_item, B, parts, amax,
+                                                                                                   arrived, h1, h2, inv);
+            CF_LAUNCH_CHECK("fmap_to_half_fused_kernel");
+        } else {
         CF_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned) * 2 * B, stream));
         // groups of batch items whose fp32 maps fit the L2 together (<= 48 MB): the conversion pass re-reads what the
         // maximum pass just read out of L2, so the feature maps cross the HBM interface once, not twice
@@ -1032,6 +1169,7 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
             CF_LAUNCH_CHECK("fmap_absmax_kernel");
             fmap_to_half_kernel<<<grid, 256, 0, stream>>>(f1, f2, per_item, B, b0, nb_, amax, h1, h2, inv);
             CF_LAUNCH_CHECK("fmap_to_half_kernel");
+        }
         }
         a = h1; bm = h2; inv_scale = inv;
     }
@@ -1061,7 +1199,13 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     }
     p.h2 = h / 4; p.w2 = w / 4; p.h3 = h / 8; p.w3 = w / 8;
     p.l2 = level2; p.l3 = level3;
-    *fused_levels = R > 0 ? 1 + p.deep : 0;
+    // wide maps (R == 2): level 2 out of pairs of tiles (kernel: pair2).  Needs an even number of target-row pairs, level-2
+    // rows that start 16-byte aligned per 32-column strip, and w1 free TMEM columns behind stage 0's accumulator
+    p.pair2 = 0;
+    if (R == 2 && p.deep == 0 && !(flags & 8) && !(flags & 64) && level2 != nullptr && aligned16(level2) && h % 4 == 0 && w % 16 == 0 &&
+        (int)align_up(R * w, 16) + w / 2 <= MAX_BN)
+        p.pair2 = 1;
+    *fused_levels = R > 0 ? 1 + (p.pair2 ? 1 : p.deep) : 0;
     p.stream_l0 = (int64_t)B * N * N * 4 > (64ll << 20);
     if (R > 0) {
         p.R = R;
@@ -1083,7 +1227,8 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
                                        : ((flags & 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
     p.atoms3d = (N % BC == 0) && !(flags & 16);
     p.b3d = p.atoms3d && (p.BN % BC == 0 || p.tiles_n == 1);
-    const int bk = f16 ? BK_F16 : BK;          // K rows per stage
+    const bool pair_req = (flags & 64) && !f16;
+    const int bk = f16 ? BK_F16 : ((pair_req || D % BK_TF32 != 0) ? BK : BK_TF32);          // K rows per stage
     const int boxb = 128 * bk;                 // bytes per TMA box
     const int a_bytes = (BM / BC) * boxb;
     p.stage_bytes = a_bytes + p.n_boxes_b * boxb;
@@ -1143,10 +1288,11 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     CF_CUDA(cudaGetDevice(&dev));
     static bool opt_in[64] = {};
     if (!opt_in[dev & 63]) {
-        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1, false, 1, BK_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1, false, 1, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<2, false, 1, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1, true, 1, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CF_CUDA(cudaFuncSetAttribute(corr_tc_kernel<1, true, 2, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         opt_in[dev & 63] = true;
     }
     const int sms = sm_count();
@@ -1164,18 +1310,19 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CF_CUDA(cudaLaunchKernelEx(&cfg, corr_tc_kernel<2, false, 1>, ta, tb, tcm, p));
+        CF_CUDA(cudaLaunchKernelEx(&cfg, corr_tc_kernel<2, false, 1, BK>, ta, tb, tcm, p));
         CF_LAUNCH_CHECK("corr_tc_kernel<pair>");
         return CF_OK;
     }
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     if (f16) {
-        if (es == 2) corr_tc_kernel<1, true, 2><<<grid, threads(2), smem_bytes, stream>>>(ta, tb, tcm, p);
-        else corr_tc_kernel<1, true, 1><<<grid, threads(1), smem_bytes, stream>>>(ta, tb, tcm, p);
+        if (es == 2) corr_tc_kernel<1, true, 2, BK><<<grid, threads(2), smem_bytes, stream>>>(ta, tb, tcm, p);
+        else corr_tc_kernel<1, true, 1, BK><<<grid, threads(1), smem_bytes, stream>>>(ta, tb, tcm, p);
         CF_LAUNCH_CHECK("corr_tc_kernel<f16>");
         return CF_OK;
     }
-    corr_tc_kernel<1, false, 1><<<grid, threads(1), smem_bytes, stream>>>(ta, tb, tcm, p);
+    if (bk == BK_TF32) corr_tc_kernel<1, false, 1, BK_TF32><<<grid, threads(1), smem_bytes, stream>>>(ta, tb, tcm, p);
+    else corr_tc_kernel<1, false, 1, BK><<<grid, threads(1), smem_bytes, stream>>>(ta, tb, tcm, p);
     CF_LAUNCH_CHECK("corr_tc_kernel");
     return CF_OK;
 }

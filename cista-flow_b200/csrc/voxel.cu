@@ -277,6 +277,11 @@ det_make_keys_kernel(const double *__restrict__ ev, const int64_t *__restrict__ 
                      uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
+    if (i >= __ldg(off + B)) {   // rows past the last window (a device-side filter kept fewer rows than the buffer holds)
+        keys[i] = invalid_key;
+        vals[i] = (uint32_t)i;
+        return;
+    }
     Window w;
     w.b = -1;
     locate_window(w, i, off, ev, B);

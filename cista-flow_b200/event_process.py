@@ -25,7 +25,13 @@ reference, all deliberate:
     ``events[:,0]`` in place, :51/:159);
   * ``event_preprocess`` returns float32 (the reference silently returns
     float64 under NumPy >= 2, SURVEY.md F9);
-  * events with (x, y) outside the grid are dropped instead of raising.
+  * events with x >= width or y >= height (or a negative coordinate) are DROPPED.  The reference does not check: its
+    NumPy variants scatter into the flattened grid at ``x + y*W + ti*W*H`` (:61-66), so an event with x == W silently
+    lands on column 0 of the next row (or of the next bin for the last row) and only an index past the end of the array
+    raises; its callers filter first (``event_window[event_window[:,1] < self.width]``, data_readers/video_readers.py:
+    208-209).  Feed pre-filtered events -- ``filter_events`` does the reader's filter on the device -- and the results
+    are identical; the divergence on unfiltered input is pinned by
+    tests/test_gpu_parity_r2.py::test_out_of_grid_events_are_dropped_where_the_reference_wraps.
 """
 from __future__ import annotations
 

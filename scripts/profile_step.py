@@ -1,29 +1,37 @@
-"""Short eager run of the configs[1] hot-path step for ncu (no graphs, no e2e)."""
+"""One hot-path step of the headline workload (BASELINE.json configs[4], this rank's share) through the public API, for ncu:
+
+    python scripts/profile_step.py [--batch 64] [--steps 2]
+
+Step k's launches are the same every step (printed: launches per step), so `ncu -s <launches per step> -c <launches per
+step>` captures exactly the second step.  No CUDA graphs here (ncu serialises launches anyway)."""
+import argparse
+import importlib.util
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench
-import cistaflow_b200 as cf
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+bench = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(bench)
 
-cfg = dict(bench.CFG)
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--config", default="configs[4]")
+args = ap.parse_args()
+from cistaflow_b200 import _lib  # noqa: E402
+
 dev = torch.device("cuda", 0)
-sets = bench.make_host_inputs(cfg, 3234)
-iters = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-import numpy as np
-dsets = []
-for s in sets:
-    d = {k: torch.from_numpy(v).to(dev) for k, v in s.items() if isinstance(v, np.ndarray)}
-    d["coords"] = [torch.from_numpy(c).to(dev) for c in s["coords"]]
-    dsets.append(d)
-for it in range(iters):
-    d = dsets[it % len(dsets)]
-    vox = cf.events_to_voxel_grid_batched(d["events"], d["offsets"], cfg["bins"], cfg["W"], cfg["H"], normalize="std",
-                                          filter_hot_pixel=True, flavour="numpy", mode="atomic")
-    blk = cf.CorrBlock(d["fmap1"], d["fmap2"], num_levels=cfg["levels"], radius=cfg["radius"])
-    outs = [blk(c) for c in d["coords"]]
-    wi, wz = cf.warp_frame_and_codes(d["img"], d["codes"], d["flow"], cfg["warp_mode"])
-torch.cuda.synchronize()
-print("profile_step done", tuple(vox.shape), tuple(outs[-1].shape), tuple(wz.shape))  # (no torch kernels in the capture)
+torch.cuda.set_device(dev)
+cfg = bench.make_cfg(args.config)
+hp = bench.HotPath(cfg, args.batch, dev, 1234 + 4000, n_sets=1)
+lib = _lib.load()
+for k in range(args.steps):
+    n0 = lib.cf_launch_count()
+    out = hp.step(hp.sets[0])
+    torch.cuda.synchronize()
+    print(f"step {k}: {lib.cf_launch_count() - n0} library launches", flush=True)
+    del out

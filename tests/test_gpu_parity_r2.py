@@ -234,3 +234,20 @@ def test_device_windowing_matches_the_reference_reader(cuda_device, n, limit):
     m = ref.shape[0]
     want = [min(i * 30000, m) for i in range(max_windows + 1)]
     assert offs_f.cpu().tolist() == want and n_f.item() == -(-m // 30000)
+
+
+def test_out_of_grid_events_are_dropped_where_the_reference_wraps(cuda_device):
+    """Round-1 ADVICE: the exact divergence on unfiltered input.  An event with x == W: the reference's NumPy voxeliser
+    wraps it onto column 0 of the next row (flat index x + y*W + ti*W*H, utils/event_process.py:61-66); this library
+    drops it -- i.e. equals the reference on the reader-filtered stream (video_readers.py:208-209)."""
+    h, w = 24, 32
+    ev = synth.events(3000, h, w, seed=9)
+    ev[100:140, 1] = w                                # x == W, rows 100..139 (never the first / last row: t0, dT unchanged)
+    ev[100:140, 2] = np.minimum(ev[100:140, 2], h - 2)
+    ev[100:140, 3] = 1.0
+    kept = ev[ev[:, 1] < w]
+    ours = cf.events_to_voxel_grid(ev, 5, w, h, mode="deterministic")
+    assert np.array_equal(bits(ours), bits(ref_port.voxel_grid_numpy(kept, 5, w, h)))
+    wrapped = ref_port.voxel_grid_numpy(ev, 5, w, h)  # what the reference returns on the unfiltered stream
+    assert not np.array_equal(wrapped, ours)
+    assert abs(float(wrapped.sum()) - float(ours.sum())) > 1.0   # the wrapped events' polarity mass is in the reference grid only
