@@ -630,7 +630,37 @@ def run_ours(args, cfg):
         barrier()
         e2e_ms_local = f0.elapsed_time(f1) / e2e_steps
         clocks = sampler.stop() if sampler else None
-        del pinned_in, pinned_out
+
+        # -- event ingest alone: host events -> H2D -> voxel grids + normalisation on the device (where
+        #    the network consumes them; the reference bins on the host and uploads the grid).  Two host formats: the
+        #    reference's fp64 rows (32 B/event) and the packed records (8 B/event, packed by the reader on the host).
+        d0 = hp.sets[0]
+        packed_host = torch.from_numpy(hp.cf.pack_events_host(d0["events"].cpu().numpy(), d0["offsets"].cpu().numpy()).view(np.int64))
+        packed_pin = pinned_write_combined(packed_host.to(dev))
+        packed_dev = torch.empty_like(packed_host, device=dev)
+        vox_buf = torch.empty_like(keep[0][0])
+        ingest = {}
+        for label, host_t, dev_t_, fn in (
+                ("fp64_rows", pinned_in[0], d0["events"], lambda: hp.voxel(d0, out=vox_buf)),
+                ("packed_8B", packed_pin, packed_dev, lambda: hp.cf.events_to_voxel_grid_packed(
+                    packed_dev, d0["offsets"], cfg["bins"], cfg["W"], cfg["H"], normalize="std", filter_hot_pixel=True, out=vox_buf))):
+            dev_t_.copy_(host_t, non_blocking=True)
+            fn()
+            torch.cuda.synchronize()
+            g_in, _ = capture(stream, fn)
+            t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            t0_.record(stream)
+            for _ in range(reps):
+                dev_t_.copy_(host_t, non_blocking=True)
+                g_in.replay()
+            t1_.record(stream)
+            torch.cuda.synchronize()
+            ms = t0_.elapsed_time(t1_) / reps
+            ingest[label] = {"ms_per_step": ms, "mevents_per_s_per_rank": B * cfg["events"] / (ms * 1e-3) / 1e6,
+                             "h2d_bytes_per_step": host_t.numel() * host_t.element_size()}
+            del g_in
+        del pinned_in, pinned_out, packed_pin, packed_dev, vox_buf
 
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -713,6 +743,9 @@ def run_ours(args, cfg):
                         "cistaflow_b200 public API (captured once as a CUDA graph) -> D2H of voxel grids, all lookup outputs, "
                         "warped frame + codes; upload / compute / read-back on three streams, two device buffer sets; "
                         "bytes are per rank"},
+        "ingest_per_rank": {**ingest, "note": "events in pinned host memory -> H2D -> voxel grids + std normalisation left on the "
+                            "device (serialised copy + kernel on one stream, rank 0's figures); fp64_rows = the reference's [N,4] float64 "
+                            "rows through cf_voxel_bin, packed_8B = host-packed records through cf_voxel_bin_packed"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roof,

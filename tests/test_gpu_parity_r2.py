@@ -251,3 +251,68 @@ def test_out_of_grid_events_are_dropped_where_the_reference_wraps(cuda_device):
     wrapped = ref_port.voxel_grid_numpy(ev, 5, w, h)  # what the reference returns on the unfiltered stream
     assert not np.array_equal(wrapped, ours)
     assert abs(float(wrapped.sum()) - float(ours.sum())) > 1.0   # the wrapped events' polarity mass is in the reference grid only
+
+
+# ------------------------------------------------- experiment paths stay correct ---
+def _run_with_env(code, env_extra):
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, **env_extra)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    return res
+
+
+def test_voxel_pipelined_launches_subprocess(cuda_device):
+    """CF_VOXEL_FLAGS bit4 (read once per process): the four L2-path stages of four consecutive chunks in one launch per
+    step (measured slower, kept selectable): same results as the default path -- bit-identical raw grids are not
+    expected (atomic order), the tolerance is the atomic mode's."""
+    code = """
+import numpy as np, torch
+import cistaflow_b200 as cf
+from cistaflow_b200 import synth, _lib
+from oracle import explicit
+dev = torch.device('cuda', 0)
+for (h, w, n, B, mb) in ((60, 80, 9000, 7, '1'), (180, 240, 15000, 5, '96')):
+    ev, off = synth.event_windows(B, n, h, w, seed=3)
+    e, o = torch.from_numpy(ev).to(dev), torch.from_numpy(off).to(dev)
+    raw = cf.events_to_voxel_grid_batched(e, o, 5, w, h, flavour='numpy', mode='atomic_l2').cpu().numpy()
+    assert _lib.load().cf_last_kernel().decode() == 'voxel_pipeline_kernel', _lib.load().cf_last_kernel()
+    fused = cf.events_to_voxel_grid_batched(e, o, 5, w, h, normalize='std', filter_hot_pixel=True, flavour='numpy',
+                                            mode='atomic_l2').cpu().numpy()
+    for b in range(B):
+        ref = explicit.voxel_grid_sequential(ev[off[b]:off[b + 1]], 5, w, h, explicit.FLAVOUR_NUMPY)
+        pos = ev[off[b]:off[b + 1]].copy(); pos[:, 3] = 1.0
+        mag = explicit.voxel_grid_sequential(pos, 5, w, h, explicit.FLAVOUR_NUMPY)
+        assert (np.abs(raw[b] - ref) <= 1e-5 * (mag + 1)).all()
+        np.testing.assert_allclose(fused[b], explicit.preprocess(ref, 'std', 5.0), rtol=1e-4, atol=1e-4)
+print('PIPE_OK')
+"""
+    # a 1 MB chunk budget forces several chunks (stages of different chunks in one launch) at the small shape
+    for mb in ("1", "96"):
+        res = _run_with_env(code, {"CF_VOXEL_FLAGS": "16", "CF_VOXEL_CHUNK_MB": mb})
+        assert res.returncode == 0 and "PIPE_OK" in res.stdout, res.stdout + res.stderr
+
+
+def test_corr_two_pass_conversion_and_lsu_stores_subprocess(cuda_device):
+    """CF_TC_FLAGS bit16 (two-pass fp16 conversion) and bit5 (fp16 kernel: level-0 rows through the LSU): experiment paths of
+    the fp16-operand pyramid build, against the fp32 SIMT kernel."""
+    code = """
+import torch
+import cistaflow_b200 as cf
+from cistaflow_b200 import synth
+dev = torch.device('cuda', 0)
+for (H, W, B) in ((480, 640, 2), (192, 256, 2)):
+    f1, f2, _ = synth.corr_inputs(B, H, W, 6)
+    a, b = torch.from_numpy(f1).to(dev), torch.from_numpy(f2).to(dev)
+    ref = cf.build_pyramid(a, b, 4, precision='fp32')
+    got = cf.build_pyramid(a, b, 4, precision='f16')
+    for l in range(4):
+        err = (got[l] - ref[l]).abs().max().item() / ref[l].abs().max().item()
+        assert err <= 1e-3, (H, W, l, err)
+print('F16_OK')
+"""
+    for flags in ("65536", "32", "128"):
+        res = _run_with_env(code, {"CF_TC_FLAGS": flags})
+        assert res.returncode == 0 and "F16_OK" in res.stdout, flags + res.stdout + res.stderr
