@@ -1253,11 +1253,19 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // epilogue warps of a lane-quarter group meeting at a named barrier; 5 store instructions per tile instead of 20):
     // 2704 against 2375 us (TF32: 2744 against 2580) -- the stores' instruction count is not what holds the epilogue up
     if (f16 && N % 4 == 0 && (flags & 32)) p.lsu_stores = 1;
+    // (c) one epilogue pass per 32-column strip of an R == 2 tile -- both level-0 boxes, level 1 and level 2 from ONE pair of
+    // TMEM loads instead of 5 chunk loads + 6 strip loads per warp, no drain between the phases: SLOWER on the same box
+    // (64 x 60x80: fp16 2668 against 2558 us, TF32 2482 against 2392 us) -- each warp then has a single pair of staging
+    // buffers in flight and waits for its bulk stores once per strip.  Removed again; the two-phase epilogue stays.
     // round 2: one SM's TMA unit moves about one 128-byte box row per ns, loads and stores alike (profiles/r02/tma_probe.txt),
     // and a 128x160 tile is 1280 operand rows + 640 level-0 rows: with fp16 operands the unit, not the tensor pipe or the
     // HBM, was suspected to set the tile period.  Measured (flags bit5 routes the fp16 kernel's level-0 rows through the LSU):
     // SLOWER, 64 x 60x80 2617 against 2515 us -- so bulk stores stay the default
     if (f16 && N % 4 == 0 && (flags & 32)) p.lsu_stores = 1;
+    // (c) one epilogue pass per 32-column strip of an R == 2 tile -- both level-0 boxes, level 1 and level 2 from ONE pair of
+    // TMEM loads instead of 5 chunk loads + 6 strip loads per warp, no drain between the phases: SLOWER on the same box
+    // (64 x 60x80: fp16 2668 against 2558 us, TF32 2482 against 2392 us) -- each warp then has a single pair of staging
+    // buffers in flight and waits for its bulk stores once per strip.  Removed again; the two-phase epilogue stays.
     // level-1 rows through shared memory into 64-byte runs (flags bit13: per-lane 16-byte stores): 64 x 24x32
     // 66.7 -> 60.8 us, 8 x 60x80 314 -> 309 us
     p.l1_staged = (p.R > 0 && p.w1 % 2 == 0 && !(flags & 8192)) ? 1 : 0;
