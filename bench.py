@@ -483,6 +483,28 @@ def other_config_line(name, dev, stream, hbm, tf32_peak, steps):
     return out
 
 
+def stock_torch_line(cfg, B, dev):
+    """the reference's own torch op sequences for this path on the same GPU (stock PyTorch CUDA kernels,
+    eager), timed beside the library on the headline workload -- scripts/stock_torch_gpu.py.  A comparator, not a path
+    of the library; a failure here must not lose the bench line."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import stock_torch_gpu
+        hp = HotPath(cfg, B, dev, 1234 + 1000 * 4, n_sets=1)
+        d, cf = hp.sets[0], hp.cf
+        vox = cf.events_to_voxel_grid_batched(d["events"], d["offsets"], cfg["bins"], cfg["W"], cfg["H"], normalize="std",
+                                              filter_hot_pixel=True, flavour="torch", mode="atomic")
+        ours = (vox, cf.CorrBlock(d["fmap1"], d["fmap2"], num_levels=cfg["levels"], radius=cfg["radius"])(d["coords"][0]),
+                *cf.warp_frame_and_codes(d["img"], d["codes"], d["flow"], cfg["warp_mode"]))
+        out = stock_torch_gpu.measure(d, cfg, ours=ours)
+        del hp, d, ours, vox
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:  # noqa: BLE001
+        torch.cuda.empty_cache()
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
 def microbench_config2(dev, stream, hbm):
     """configs[2]: voxel-binning + forward-splat warp microbench at 346x260, 5 bins, 50k events/window,
     batched x1 / x64 / x1024 windows (separates launch latency from bandwidth)."""
@@ -688,11 +710,12 @@ def run_ours(args, cfg):
         return
 
     # -- single-GPU extras: the other BASELINE configs and the CPU baseline (rank 0 of a 1-GPU run only)
-    other, cpu = None, None
+    other, cpu, stock = None, None, None
     if world == 1:
         del graphs, keep, hp
         torch.cuda.empty_cache()
         if not args.no_extra:
+            stock = stock_torch_line(cfg, B, dev)
             other = {}
             with torch.cuda.stream(stream):
                 for name in ("configs[0]", "configs[1]", "configs[3]"):
@@ -756,6 +779,7 @@ def run_ours(args, cfg):
         "kernels": kernels,
         "tf32_peak_measured_tflops": tf32_peak,
         "other_configs": other,
+        "stock_torch_gpu": stock,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "per_rank_ms": {"step": table[:, 0].tolist(), "e2e_step": table[:, 1].tolist()},

@@ -71,3 +71,32 @@ def test_reference_arm_prints_the_same_config_and_honours_steps(bench):
     res2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                           capture_output=True, text=True, timeout=120, env=env2, cwd=ROOT)
     assert res2.returncode == 0 and res2.stdout.strip() == ""
+
+
+def test_stock_torch_comparator_restates_the_reference_ops():
+    """scripts/stock_torch_gpu.py (the same-GPU stock-PyTorch comparator of SURVEY.md 8d) must compute what the
+    reference computes: its op sequences against the pinned oracle, on CPU at a small size."""
+    sys.path.insert(0, ROOT)
+    from cistaflow_b200 import synth
+    from oracle import ref_port
+    spec = importlib.util.spec_from_file_location("stock_torch_gpu", os.path.join(ROOT, "scripts", "stock_torch_gpu.py"))
+    st = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(st)
+    H, W, nb = 64, 96, 5
+    ev, off = synth.event_windows(2, 3000, H, W, 77)
+    got = st.voxel_step(torch.from_numpy(ev.copy()), off.tolist(), nb, W, H)
+    for b in range(2):
+        want = ref_port.preprocess_torch(ref_port.voxel_grid_torch(torch.from_numpy(ev[off[b]:off[b + 1]].copy()), nb, W, H), "std", True)
+        assert torch.equal(got[b], want)
+    img, codes, flow = synth.warp_inputs(2, H, W, 78, 16, flow_kind="smooth")
+    img, codes, flow = map(torch.from_numpy, (img, codes, flow))
+    for mode, sign in (("forward", -1.0), ("backward", 1.0)):
+        wi, wz = st.warp_step(img, codes, flow, (st.StockWarp(W, H, sign), st.StockWarp(W // 2, H // 2, sign)))
+        ri, rz = ref_port.warp_frame_and_codes(img, codes, flow, mode)
+        assert torch.equal(wi, ri) and torch.equal(wz, rz)
+    f1, f2, c0 = synth.corr_inputs(2, 128, 192, 79)     # 16x24 map: the coarsest level is 2x3 (1x1 divides by zero)
+    f1, f2, c0 = map(torch.from_numpy, (f1, f2, c0))
+    pyr = st.pyramid_step(f1, f2, 4)
+    ref = ref_port.corr_pyramid(f1, f2, 4)
+    assert all(torch.equal(a, b) for a, b in zip(pyr, ref))
+    assert torch.allclose(st.lookup_step(pyr, c0, 4), ref_port.corr_lookup(ref, c0, 4), rtol=0, atol=1e-5)
