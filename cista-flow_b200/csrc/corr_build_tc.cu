@@ -1253,15 +1253,18 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // epilogue warps of a lane-quarter group meeting at a named barrier; 5 store instructions per tile instead of 20):
     // 2704 against 2375 us (TF32: 2744 against 2580) -- the stores' instruction count is not what holds the epilogue up
     if (f16 && N % 4 == 0 && (flags & 32)) p.lsu_stores = 1;
-    // (c) one epilogue pass per 32-column strip of an R == 2 tile -- both level-0 boxes, level 1 and level 2 from ONE pair of
-    // TMEM loads instead of 5 chunk loads + 6 strip loads per warp, no drain between the phases: SLOWER on the same box
-    // (64 x 60x80: fp16 2668 against 2558 us, TF32 2482 against 2392 us) -- each warp then has a single pair of staging
-    // buffers in flight and waits for its bulk stores once per strip.  Removed again; the two-phase epilogue stays.
-    // round 2: one SM's TMA unit moves about one 128-byte box row per ns, loads and stores alike (profiles/r02/tma_probe.txt),
-    // and a 128x160 tile is 1280 operand rows + 640 level-0 rows: with fp16 operands the unit, not the tensor pipe or the
-    // HBM, was suspected to set the tile period.  Measured (flags bit5 routes the fp16 kernel's level-0 rows through the LSU):
-    // SLOWER, 64 x 60x80 2617 against 2515 us -- so bulk stores stay the default
-    if (f16 && N % 4 == 0 && (flags & 32)) p.lsu_stores = 1;
+    // (d) what the data movement alone costs (scripts/experiments/write_probe.cu -> profiles/r02/write_probe.txt, no MMAs, no
+    // epilogue arithmetic, per 128x160 tile and SM): the two 80 KB operand stages 1.12 us; the 20 level-0 boxes 2.4-2.5 us
+    // (4.9-5.0 TB/s chip-wide, the same with 2 CTAs per SM or 2-atom boxes: ~3.75 ns per 128-byte box row); both together
+    // 3.27 us -- the TMA unit mostly serialises them, and the kernel's 3.75 us per tile (with levels 1-2 on top) is within 15 %
+    // of that.  A write-only stream reaches 6.1-6.2 TB/s (memset 7.0), one bulk store per whole 640-byte tile row 5.9 TB/s,
+    // loads + row stores 2.5 us per tile.  Two epilogues built on row stores (padded row-major staging, 16 rows per lane
+    // quarter single-buffered / 8 rows double-buffered, the warp pair of a quarter meeting at a named barrier, lanes issuing
+    // their rows) passed the parity tests and were SLOWER: 2685 / 3350 against 2100-2190 us at 64 x 60x80 -- beside two 80 KB
+    // operand stages only 64 KB are left, a lane quarter's rows (20 KB) cannot all be staged at once, and the extra passes
+    // (barriers, TMEM re-reads at the register cap of 168) lengthen the epilogue's serial chain more than the cheaper stores
+    // shorten the TMA queue.  (e) level-0 chunks split between TMA (half-0 warps) and LSU (half-1 warps) or the reverse:
+    // 2280 / 2318 against 2190 us.  All removed again.
     // (c) one epilogue pass per 32-column strip of an R == 2 tile -- both level-0 boxes, level 1 and level 2 from ONE pair of
     // TMEM loads instead of 5 chunk loads + 6 strip loads per warp, no drain between the phases: SLOWER on the same box
     // (64 x 60x80: fp16 2668 against 2558 us, TF32 2482 against 2392 us) -- each warp then has a single pair of staging
