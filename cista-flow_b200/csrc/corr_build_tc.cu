@@ -618,6 +618,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_after();
             if (tile_no == 0 && threadIdx.x == 0) stamp(20);
             if (threadIdx.x == 0) TC_TRACE(tile_no, 12);
+            if (threadIdx.x == 128 && kblocks <= 2) TC_TRACE(tile_no, 5);   // (second warp of lane quarter 0; the slots of K blocks 2.. are free)
             if (p.ablate & 16) {  // experiment: the epilogue reads nothing (MMA issue rate without TMEM read traffic)
                 tc_fence_before();
                 if (CL == 2) mbar_arrive_cluster(mapa_rank0(&tempty[acc]));
@@ -700,6 +701,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (row_ok && bn_valid > 0) store_row_chunk(l0row + j0, v, scale, bn_valid, vec4_l0 && (bn_valid % 4 == 0), false);
             }
             if (threadIdx.x == 0) TC_TRACE(tile_no, 13);
+            if (threadIdx.x == 128 && kblocks <= 2) TC_TRACE(tile_no, 6);
             // ---- level 1: 2x2 means straight from the accumulator rows
             if (p.R != 0 && !(p.ablate & 32)) {
                 const int y0 = nb * p.R;
@@ -870,6 +872,11 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             else mbar_arrive(&tempty[acc]);
             if (tile_no == 0 && threadIdx.x == 0) stamp(21);
             if (threadIdx.x == 0) TC_TRACE(tile_no, 14);
+            if (kblocks <= 2) {
+                if (threadIdx.x == 128) TC_TRACE(tile_no, 7);
+                if (threadIdx.x == 96) TC_TRACE(tile_no, 8);
+                if (threadIdx.x == 224) TC_TRACE(tile_no, 9);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -1264,7 +1271,13 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // operand stages only 64 KB are left, a lane quarter's rows (20 KB) cannot all be staged at once, and the extra passes
     // (barriers, TMEM re-reads at the register cap of 168) lengthen the epilogue's serial chain more than the cheaper stores
     // shorten the TMA queue.  (e) level-0 chunks split between TMA (half-0 warps) and LSU (half-1 warps) or the reverse:
-    // 2280 / 2318 against 2190 us.  All removed again.
+    // 2280 / 2318 against 2190 us.  (f) other splits of the 5 chunks between the two warps of a lane quarter than the
+    // alternating 3 | 2 (the second warp also takes 2 of the 3 pooling strips): 4 | 1 2256-2276, 2 | 3 2240, 5 | 0 2372 against
+    // 2197 us.  All removed again.  What the per-tile timeline shows (scripts/corr_trace.py with the stamps of four epilogue
+    // warps, profiles/r02/corr_trace_f16_8x60x80.txt): an epilogue warp is busy 2.75-3.0 us per tile and then WAITS 0.6-0.9 us for
+    // the next accumulator; the tile period (3.6-3.9 us) is the chain  accumulator drained by all 8 warps -> operand stages
+    // of the tile after next land (the ring of two 80 KB stages holds exactly one tile's K, and these loads queue in the TMA
+    // unit behind the store boxes) -> its MMAs run (~2 us, bound by the operand fetch from shared memory) -> epilogue.
     // (c) one epilogue pass per 32-column strip of an R == 2 tile -- both level-0 boxes, level 1 and level 2 from ONE pair of
     // TMEM loads instead of 5 chunk loads + 6 strip loads per warp, no drain between the phases: SLOWER on the same box
     // (64 x 60x80: fp16 2668 against 2558 us, TF32 2482 against 2392 us) -- each warp then has a single pair of staging

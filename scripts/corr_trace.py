@@ -37,6 +37,7 @@ for c in ctas:
         if r[12] == 0 and r[2] == 0 and r[0] == 0:
             break
         u = lambda v: (v - t0) / 1e3 if v else float('nan')
-        land = " ".join(f"{u(v):6.2f}" for v in r[3:11])
+        land = " ".join(f"{u(v):6.2f}" for v in r[3:5])
+        w4 = f" || warp4 ready {u(r[5]):6.2f} l0 {u(r[6]):6.2f} done {u(r[7]):6.2f} | warp3 done {u(r[8]):6.2f} warp7 done {u(r[9]):6.2f}" if r[7] else ""
         print(f"  tile {k:2d}: loads {u(r[0]):6.2f}..{u(r[1]):6.2f} | acc free {u(r[2]):6.2f} landed [{land}] commit {u(r[11]):6.2f} "
-              f"| epi ready {u(r[12]):6.2f} l0 issued {u(r[13]):6.2f} done {u(r[14]):6.2f}")
+              f"| epi ready {u(r[12]):6.2f} l0 issued {u(r[13]):6.2f} done {u(r[14]):6.2f}{w4}")

@@ -162,10 +162,10 @@ __global__ void __launch_bounds__(128) row_full_kernel(float *dst, int B, int N,
 // {64 x 128 x 3} (fmap2 slice) into a ring of two, freed as soon as they land); warps 0-7 store the tile's level 0:
 // STORE 0: nothing, 1: 32x32 boxes (8 warps, the kernel's epilogue), 2: whole 640-byte rows (4 warps, each lane its row).
 // Tile order = the kernel's (nb fastest, interleaved over the grid) or, with A_RES, runs of 15 consecutive nb per CTA.
-template <int STORE, bool A_RES, bool LOADS>
-__global__ void __launch_bounds__(288) move_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_c,
+template <int STORE, bool A_RES, int LOADS>
+__global__ void __launch_bounds__(320) move_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_c,
             const __grid_constant__ CUtensorMap tmap_c2, const __grid_constant__ CUtensorMap tmap_c5,
-                                                   float *dst, int B, int N, int BN) {
+                                                   float *dst, const void *dst_aux, int B, int N, int BN) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full[2];
     constexpr int A_BYTES = 2 * 64 * 128 * 2, B_BYTES = 3 * 64 * 128 * 2, STAGE = A_BYTES + B_BYTES;
@@ -180,8 +180,43 @@ __global__ void __launch_bounds__(288) move_kernel(const __grid_constant__ CUten
         if (!A_RES) return blockIdx.x + k * gridDim.x;
         return ((long long)blockIdx.x + (k / RUN) * gridDim.x) * RUN + k % RUN;
     };
-    if (warp == 8) {
-        if (!LOADS || lane != 0) return;
+    if (warp >= 8 && LOADS == 2) {
+        // operand stages through the LSU: cp.async 16 B pieces into the layout the TMA would have produced (128B swizzle),
+        // one commit group per stage, two stages in flight
+        const unsigned short *fm = reinterpret_cast<const unsigned short *>(dst_aux);
+        const int lw = warp - 8, nlw = (int)(blockDim.x >> 5) - 8;
+        long long kk = 0;
+        for (long long k = 0; tile_at(k) < total; ++k) {
+            const long long tile = tile_at(k);
+            const int nb = (int)(tile % tiles_n);
+            const long long t = tile / tiles_n;
+            const int mb = (int)(t % tiles_m), b = (int)(t / tiles_m);
+            for (int kb = 0; kb < 2; ++kb, ++kk) {
+                uint8_t *sa = stage_mem + (kk & 1) * STAGE, *sb = sa + A_BYTES;
+                const size_t row0 = (size_t)b * 256 + kb * 128;
+                for (int c = lw * 32 + lane; c < 2048; c += 32 * nlw) {
+                    const int kr = c >> 4, cc = c & 15;
+                    int col = mb * 128 + cc * 8;
+                    if (col > N - 8) col = N - 8;
+                    const void *src = fm + (row0 + kr) * N + col;
+                    const uint32_t d = smem_u32(sa + (cc >> 3) * 16384 + kr * 128 + (((cc & 7) ^ (kr & 7)) << 4));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+                }
+                for (int c = lw * 32 + lane; c < 2560; c += 32 * nlw) {
+                    const int kr = c / 20, cc = c % 20;
+                    const void *src = fm + (row0 + kr) * N + nb * BN + cc * 8;
+                    const uint32_t d = smem_u32(sb + (cc >> 3) * 16384 + kr * 128 + (((cc & 7) ^ (kr & 7)) << 4));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
+    if (warp >= 8) {
+        if (warp > 8 || LOADS != 1 || lane != 0) return;
         uint32_t phase_bits = 0;
         long long issued = 0, waited = 0;
         long long my_tiles = 0;
@@ -381,20 +416,22 @@ int main(int argc, char **argv) {
         }
 #define RUNMOVE(NAME, ST, AR, LD, SM)                                                                                        \
         CK(cudaFuncSetAttribute(move_kernel<ST, AR, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));                   \
-        timed(NAME, (double)bytes, [&] { move_kernel<ST, AR, LD><<<148, 288, SM>>>(mfa, mf, m, mc2, mc5, (float *)buf, B, N, BN); });
-        RUNMOVE("loads only", 0, false, true, sm_box)
-        RUNMOVE("loads only, A resident", 0, true, true, sm_box)
-        RUNMOVE("box stores only", 1, false, false, sm_box)
-        RUNMOVE("loads + box stores", 1, false, true, sm_box)
-        RUNMOVE("A-res loads + box", 1, true, true, sm_box)
-        RUNMOVE("2-atom boxes only", 3, false, false, sm_box)
-        RUNMOVE("loads + 2-atom boxes", 3, false, true, sm_box)
-        RUNMOVE("5-atom boxes only", 4, false, false, sm_box)
-        RUNMOVE("loads + 5-atom boxes", 4, false, true, sm_box)
+        timed(NAME, (double)bytes, [&] { move_kernel<ST, AR, LD><<<148, (LD == 2 ? 320 : 288), SM>>>(mfa, mf, m, mc2, mc5, (float *)buf, fm, B, N, BN); });
+        RUNMOVE("loads only", 0, false, 1, sm_box)
+        RUNMOVE("loads only, A resident", 0, true, 1, sm_box)
+        RUNMOVE("box stores only", 1, false, 0, sm_box)
+        RUNMOVE("loads + box stores", 1, false, 1, sm_box)
+        RUNMOVE("A-res loads + box", 1, true, 1, sm_box)
+        RUNMOVE("LSU loads only (2 warps)", 0, false, 2, sm_box)
+        RUNMOVE("LSU loads + box stores", 1, false, 2, sm_box)
+        RUNMOVE("2-atom boxes only", 3, false, 0, sm_box)
+        RUNMOVE("loads + 2-atom boxes", 3, false, 1, sm_box)
+        RUNMOVE("5-atom boxes only", 4, false, 0, sm_box)
+        RUNMOVE("loads + 5-atom boxes", 4, false, 1, sm_box)
         if (sm_row <= 227 * 1024) {
-            RUNMOVE("row stores only", 2, false, false, sm_row)
-            RUNMOVE("loads + row stores", 2, false, true, sm_row)
-            RUNMOVE("A-res loads + row", 2, true, true, sm_row)
+            RUNMOVE("row stores only", 2, false, 0, sm_row)
+            RUNMOVE("loads + row stores", 2, false, 1, sm_row)
+            RUNMOVE("A-res loads + row", 2, true, 1, sm_row)
         } else printf("row staging does not fit beside two 80 KB stages (%d B)\n", sm_row);
         CK(cudaFree(fm));
     }
