@@ -89,6 +89,14 @@ struct Params {
     int tiles_mp;  // pair kernel: pairs of query tiles per batch item (= ceil(tiles_m / 2)); total_tiles counts pairs
     int stages;      // shared-memory ring depth
     int stage_bytes; // A_BYTES + n_boxes_b * BOX_BYTES
+    int qbox_h0;     // qbox: level-0 chunks of the first warp of a lane quarter
+    int qbox;        // 1 (two epilogue warps per lane quarter): level 0 leaves as ONE {32 cols, 32 rows, BN/32 atoms} box per lane
+                     // quarter and tile (tmap_c is then that 3-D map over {32, B*N rows, N/32 atoms}) -- see launch_tc()
+    int epi_bytes;   // bytes of epilogue buffers between the operand ring and the barriers
+    int l1_scratch;  // byte offset (from the epilogue buffers) of a level-1 scratch area of 2 KB per epilogue warp that is NOT a
+                     // level-0 box buffer (0: none, the strips borrow a box buffer and wait for its store)
+    int b_sw64;      // fp16 operands, BN_mma an odd multiple of 32: the fmap2 slice as {32 cols, K rows, BN_mma / 32 atoms} with the
+                     // 64-byte swizzle -- exactly BN_mma columns per stage instead of the next multiple of 64 (160: 40 KB, not 48)
     int ablate;    // experiments (CF_TC_FLAGS bits 8-10): 1 = no level-0/1 stores, 2 = no MMAs, 4 = no operand loads, 16 = no epilogue at all, 32 = no pooling part, 64 = no level-0 part
     int b_half;    // pair kernel: fmap2 boxes per stage and CTA (half of the tile's columns each)
     int h1, w1;    // level-1 map size
@@ -203,6 +211,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *s
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// the two epilogue warps of TMEM lane quarter q (64 threads) meet
+__device__ __forceinline__ void quarter_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // at most N committed store groups may still be READING their shared-memory source
 template <int N>
@@ -414,7 +424,11 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     static_assert(!(F16 && CL == 2), "the CTA-pair variant is tf32 only");
     constexpr int EPI_SPLIT = ES, EPI_WARPS = 4 * ES, EPI_BYTES = epi_bytes(ES);
+#ifdef CF_SWAP_SERVICE_WARPS   // experiment: which warp scheduler (warp % 4) hosts the producer / the MMA issuer
+    constexpr int PRODUCER_WARP = EPI_WARPS + 1, MMA_WARP = EPI_WARPS;
+#else
     constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+#endif
     constexpr int BC = F16 ? 64 : 32;                   // operand columns per TMA box (128 bytes)
     constexpr int BKK = F16 ? BK_F16 : BKT;             // K rows per stage (TF32: 64, or 32 for D % 64 != 0 and the CTA-pair kernel)
     constexpr int BOXB = 128 * BKK;                     // bytes of one TMA box: 128-byte rows x BKK
@@ -423,7 +437,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int KSTEP = F16 ? 2048 : 1024;            // descriptor start-address advance per MMA
     const int STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
     uint8_t *epi = smem + STAGES * STAGE_BYTES;  // [EPI_WARPS][2][EPI_BUF_BYTES]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(epi + EPI_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi + p.epi_bytes);
     uint64_t *full = bars, *empty = bars + MAX_STAGES;
     uint64_t *tfull = bars + 2 * MAX_STAGES, *tempty = bars + 2 * MAX_STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
@@ -434,8 +448,28 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int first_tile = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
     // the s-th tile of this CTA: tile indices have the target-row pair nb fastest, so with pair2 a CTA takes the two tiles
     // 2u, 2u+1 of unit u back to back (same batch item, same query rows, target rows 4u' .. 4u'+3)
-    const int GS = p.pair2 ? 2 : 1;
-    auto tile_of = [&](int sq) { return GS * (first_tile + (sq / GS) * tile_step) + (sq % GS); };
+    const int GS = p.pair2 ? 2 : 1, gs_shift = p.pair2 ? 1 : 0;
+    auto tile_of = [&](int sq) { return ((first_tile + (sq >> gs_shift) * tile_step) << gs_shift) + (sq & (GS - 1)); };
+    // (b, mb, nb) of the next tile of this CTA without integer divisions (three of them per tile, twice with the look-ahead
+    // of the fp16 epilogue, were ~0.5 us of every tile's serial chain): the step from the last tile of a group to the first
+    // of the next is a constant, decomposed once
+    const int jump = GS * tile_step - (GS - 1);
+    const int jump_n = jump % p.tiles_n, jump_m = (jump / p.tiles_n) % p.tiles_m, jump_b = (jump / p.tiles_n) / p.tiles_m;
+    auto advance = [&](int sq, int &tile, int &b, int &mb, int &nb) {   // tile of sequence number sq -> sq + 1   (CL == 1)
+        if (GS == 2 && !(sq & 1)) {   // second tile of a pair: the next target-row pair (tiles_n is even with pair2)
+            ++tile;
+            ++nb;
+            return;
+        }
+        tile += jump;
+        nb += jump_n;
+        int c = nb >= p.tiles_n ? 1 : 0;
+        nb -= c ? p.tiles_n : 0;
+        mb += jump_m + c;
+        c = mb >= p.tiles_m ? 1 : 0;
+        mb -= c ? p.tiles_m : 0;
+        b += jump_b + c;
+    };
     if (threadIdx.x == 0) stamp(0);
 
     if (warp == PRODUCER_WARP && lane == 0) {
@@ -469,13 +503,14 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             // pair kernel: the leader's barrier counts the bytes of BOTH CTAs' boxes
-            const uint32_t tx_bytes = (uint32_t)(CL * (BM / BC + (CL == 2 ? p.b_half : p.n_boxes_b))) * BOXB;
+            const uint32_t tx_bytes = (F16 && p.b_sw64) ? (uint32_t)p.stage_bytes
+                                                       : (uint32_t)(CL * (BM / BC + (CL == 2 ? p.b_half : p.n_boxes_b))) * BOXB;
             const int jr = CL == 2 ? rank * (p.BN_mma / 2) : 0;  // first fmap2 column of this CTA inside the tile
             int tile_no = 0;
-            for (int tile = tile_of(0); tile < p.total_tiles; tile = tile_of(++tile_no)) {
-                int b, mb, nb;
+            int tile = tile_of(0), b = 0, mb = 0, nb = 0;
+            if (CL == 1 && tile < p.total_tiles) decode_tile(p, tile, b, mb, nb);
+            for (; tile < p.total_tiles; ++tile_no) {
                 if (CL == 2) decode_pair_tile(p, tile, rank, b, mb, nb);
-                else decode_tile(p, tile, b, mb, nb);
                 const int i0 = mb * BM, j0 = nb * p.BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -522,7 +557,9 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                         for (int a = 0; a < BM / BC; ++a) tma_load_2d(sa + a * BOXB, &tmap_a, i0 + BC * a, krow, &full[stage]);
                     }
-                    if (p.b3d) {
+                    if (F16 && p.b_sw64) {
+                        tma_load_3d(sb, &tmap_b, 0, krow, j0 / 32, &full[stage]);
+                    } else if (p.b3d) {
                         tma_load_3d(sb, &tmap_b, 0, krow, j0 / BC, &full[stage]);
                     } else {
                         for (int a = 0; a < p.n_boxes_b; ++a) tma_load_2d(sb + a * BOXB, &tmap_b, j0 + BC * a, krow, &full[stage]);
@@ -531,6 +568,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (CL == 2) tile = tile_of(tile_no + 1);
+                else advance(tile_no, tile, b, mb, nb);
             }
         }
     } else if (warp == MMA_WARP) {
@@ -547,6 +586,12 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t desc_hi = F16 ? (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29))
                                          : (uint32_t)((512u >> 4) | (1u << 14) | (1u << 29));
             const uint32_t lbo_bits = ((uint32_t)BOXB >> 4) << 16;   // bytes between column atoms = one TMA box
+            // fmap2 slice in the 64-byte swizzle (b_sw64): atoms of 32 columns x 64 B rows, 8-row groups 512 B apart, one
+            // atom = BKK x 64 B, and a K step of 16 rows is 1024 B
+            const bool sw64 = F16 && p.b_sw64;
+            const uint32_t desc_hi_b = sw64 ? (uint32_t)((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi;
+            const uint32_t lbo_bits_b = sw64 ? (((uint32_t)(BKK * 64) >> 4) << 16) : lbo_bits;
+            const uint32_t kstep_b = sw64 ? (1024u >> 4) : (uint32_t)(KSTEP >> 4);
             const uint32_t smem_base = smem_u32(smem);
             int tile_no = 0;
             for (int tile = tile_of(0); tile < p.total_tiles; tile = tile_of(++tile_no)) {
@@ -562,13 +607,13 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         if (kb < 8) TC_TRACE(tile_no, 3 + kb);
                     }
                     const uint32_t sa = smem_base + (uint32_t)(stage * STAGE_BYTES);
-                    const uint32_t a_lo = (((sa & 0x3FFFFu) >> 4) | lbo_bits), b_lo = ((((sa + ABYTES) & 0x3FFFFu) >> 4) | lbo_bits);
+                    const uint32_t a_lo = (((sa & 0x3FFFFu) >> 4) | lbo_bits), b_lo = ((((sa + ABYTES) & 0x3FFFFu) >> 4) | lbo_bits_b);
                     if (elect_one()) {
                         if (!(p.ablate & 2)) {
 #pragma unroll
                             for (int kk = 0; kk < MMAS; ++kk) {
                                 const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)(kk * (KSTEP >> 4)));
-                                const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)(kk * (KSTEP >> 4)));
+                                const uint64_t db = ((uint64_t)desc_hi_b << 32) | (uint64_t)(b_lo + (uint32_t)kk * kstep_b);
                                 if (F16) umma_f16(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
                                 else if (CL == 2) umma_tf32_2sm(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
                                 else umma_tf32(d_tmem, da, db, idesc, (uint32_t)((kb | kk) != 0));
@@ -606,19 +651,38 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool vec4_l1 = (p.w1 % 4) == 0;
         uint8_t *my_epi = epi + warp * 2 * EPI_BUF_BYTES;
         int tile_no = 0;
-        for (int tile = tile_of(0); tile < p.total_tiles; tile = tile_of(++tile_no)) {
-            int b, mb, nb;
+        // F16: 1/sqrt(D) times the powers of two that undo the per-item scaling of the operands.  The two factors of the NEXT
+        // tile's item are fetched while this tile is drained: the volume streams through the L2, so these loads are DRAM
+        // misses, and fetched at the top of their own tile they put ~0.9 us into every tile of the slowest epilogue warp --
+        // which sets the tile period (corr_trace, round 2)
+        float inv_a = 1.f, inv_b = 1.f;
+        int tile = tile_of(0), b = 0, mb = 0, nb = 0;
+        if (CL == 1 && tile < p.total_tiles) decode_tile(p, tile, b, mb, nb);
+        int tile_nx = tile, b_nx = b, mb_nx = mb, nb_nx = nb;      // the tile after this one (CL == 1)
+        if (CL == 1) advance(0, tile_nx, b_nx, mb_nx, nb_nx);
+        if (F16 && tile < p.total_tiles) {
+            inv_a = __ldg(p.inv_scale + b);
+            inv_b = __ldg(p.inv_scale + p.B + b);
+        }
+        auto next_tile = [&]() {
+            ++tile_no;
+            if (CL == 2) { tile = tile_of(tile_no); return; }
+            tile = tile_nx; b = b_nx; mb = mb_nx; nb = nb_nx;
+            advance(tile_no, tile_nx, b_nx, mb_nx, nb_nx);
+        };
+        for (; tile < p.total_tiles; next_tile()) {
             if (CL == 2) decode_pair_tile(p, tile, rank, b, mb, nb);
-            else decode_tile(p, tile, b, mb, nb);
             const int i = mb * BM + row;
             const bool row_ok = i < p.N;
-            // 1/sqrt(D), times the powers of two that undo the per-item scaling of the fp16 operands
-            const float scale = F16 ? p.scale * __ldg(p.inv_scale + b) * __ldg(p.inv_scale + p.B + b) : p.scale;
+            const float scale = F16 ? p.scale * inv_a * inv_b : p.scale;
+            if (F16 && tile_nx < p.total_tiles) {
+                inv_a = __ldg(p.inv_scale + b_nx);
+                inv_b = __ldg(p.inv_scale + p.B + b_nx);
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             if (tile_no == 0 && threadIdx.x == 0) stamp(20);
             if (threadIdx.x == 0) TC_TRACE(tile_no, 12);
-            if (threadIdx.x == 128 && kblocks <= 2) TC_TRACE(tile_no, 5);   // (second warp of lane quarter 0; the slots of K blocks 2.. are free)
             if (p.ablate & 16) {  // experiment: the epilogue reads nothing (MMA issue rate without TMEM read traffic)
                 tc_fence_before();
                 if (CL == 2) mbar_arrive_cluster(mapa_rank0(&tempty[acc]));
@@ -633,7 +697,36 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // ---- level 0: TMEM -> registers (x scale) -> swizzled smem box -> TMA bulk store.
             // A warp-wide st.global of this fragment would touch 32 different rows per instruction
             // (measured: 18k cycles per tile); the TMA writes whole 128-byte lines instead.
-            if (bn_valid >= 32 && !(p.ablate & 64)) {
+            if (p.qbox && !(p.ablate & 64)) {
+                // ---- level 0, one box per lane quarter: the SM's TMA unit carries the operand stages and the volume's stores
+                // and is ~90 % busy (profiles/r02/write_probe.txt, corr_trace_f16_8x60x80.txt); twenty {32 x 32} boxes per tile cost
+                // it 2.4 us, four {32 x 32 x 5} boxes 1.5 us.  The two warps of the quarter stage their chunks (same swizzled
+                // 4 KB images as below) side by side, meet, and one lane stores all of them.
+                uint8_t *qb = epi + quarter * (p.BN / 32) * EPI_BUF_BYTES;
+                const bool issuer = half == 0 && lane == 0;
+                if (issuer) tma_store_wait_read<0>();      // the previous tile's box has left the buffer
+                quarter_barrier(quarter);
+                // chunks [0, qbox_h0) to the first warp, the rest to the second (which also takes the odd pooling strip)
+                for (int ci = half ? p.qbox_h0 : 0; ci < (half ? p.BN / 32 : p.qbox_h0); ++ci) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + 32 * ci, v);
+                    tmem_ld_wait();
+                    uint8_t *buf = qb + ci * EPI_BUF_BYTES;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 o = make_float4(__uint_as_float(v[4 * q]) * scale, __uint_as_float(v[4 * q + 1]) * scale,
+                                                     __uint_as_float(v[4 * q + 2]) * scale, __uint_as_float(v[4 * q + 3]) * scale);
+                        *reinterpret_cast<float4 *>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+                    }
+                }
+                fence_async_smem();
+                quarter_barrier(quarter);
+                if (issuer) {
+                    if (mb * BM + 32 * quarter < p.N && !(p.ablate & 1))
+                        tma_store_3d(&tmap_c, qb, 0, b * p.N + mb * BM + 32 * quarter, j0 >> 5);
+                    tma_store_commit();
+                }
+            } else if (bn_valid >= 32 && !(p.ablate & 64)) {
                 const int nchunks = (bn_valid + 31) / 32;
                 for (int ci = half; ci < nchunks; ci += EPI_SPLIT) {
                     const int c0 = min(ci * 32, bn_valid - 32);  // last chunk overlaps its neighbour (same values)
@@ -701,7 +794,6 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (row_ok && bn_valid > 0) store_row_chunk(l0row + j0, v, scale, bn_valid, vec4_l0 && (bn_valid % 4 == 0), false);
             }
             if (threadIdx.x == 0) TC_TRACE(tile_no, 13);
-            if (threadIdx.x == 128 && kblocks <= 2) TC_TRACE(tile_no, 6);
             // ---- level 1: 2x2 means straight from the accumulator rows
             if (p.R != 0 && !(p.ablate & 32)) {
                 const int y0 = nb * p.R;
@@ -730,8 +822,9 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             // the lane's 16 values (64 B of ITS row) -> shared memory -> whole 64-byte runs, 8 rows per
                             // store instruction (lane <-> row 8*it + lane/4, piece lane%4) instead of 32 rows x 16 B
                             const int npool = min(16, p.w1 - (xc >> 1));
-                            float *stg = reinterpret_cast<float *>(my_epi);
-                            if (!p.lsu_stores && lane == 0) tma_store_wait_read<0>();   // the level-0 boxes have left the buffers
+                            float *stg = p.l1_scratch ? reinterpret_cast<float *>(epi + p.l1_scratch + warp * 2048)
+                                                      : reinterpret_cast<float *>(my_epi);
+                            if (!p.l1_scratch && !p.lsu_stores && lane == 0) tma_store_wait_read<0>();   // the level-0 boxes have left the buffers
                             __syncwarp();
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
@@ -872,11 +965,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             else mbar_arrive(&tempty[acc]);
             if (tile_no == 0 && threadIdx.x == 0) stamp(21);
             if (threadIdx.x == 0) TC_TRACE(tile_no, 14);
-            if (kblocks <= 2) {
-                if (threadIdx.x == 128) TC_TRACE(tile_no, 7);
-                if (threadIdx.x == 96) TC_TRACE(tile_no, 8);
-                if (threadIdx.x == 224) TC_TRACE(tile_no, 9);
-            }
+            if (kblocks <= 2 && lane == 0 && warp > 0) TC_TRACE(tile_no, warp == 3 ? 15 : (warp < 3 ? 4 + warp : 3 + warp));   // (slots of K blocks 2.. are free: epilogue done, warps 1,2 -> 5,6; 4..7 -> 7..10; 3 -> 15)
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -1085,6 +1174,36 @@ static int make_fmap_tmap3(CUtensorMap *m, const void *base, int B, int D, int N
     return CF_OK;
 }
 
+// the level-0 volume as {32 cols, B*N rows, N/32 column atoms} (N % 32 == 0): a box {32, 32, atoms} stores `atoms` swizzled
+// 32 x 32 images that lie side by side in shared memory with ONE instruction
+static int make_volume_tmap_atoms(CUtensorMap *m, float *base, int B, int N, int atoms) {
+    EncodeTiledFn fn = encode_fn();
+    CF_REQUIRE(fn, CF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {32, (cuuint64_t)B * N, (cuuint64_t)N / 32};
+    cuuint64_t strides[2] = {(cuuint64_t)N * sizeof(float), 128};
+    cuuint32_t box[3] = {32, 32, (cuuint32_t)atoms};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_CUDA, "cuTensorMapEncodeTiled (volume, atoms) failed with CUresult %d", (int)r);
+    return CF_OK;
+}
+
+// fp16 feature map as {32 cols, B*D rows, N/32 atoms of 64 bytes}, 64-byte swizzle (N % 32 == 0)
+static int make_fmap_tmap3_sw64(CUtensorMap *m, const void *base, int B, int D, int N, int box_rows, int box_atoms) {
+    EncodeTiledFn fn = encode_fn();
+    CF_REQUIRE(fn, CF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {32, (cuuint64_t)B * D, (cuuint64_t)N / 32};
+    cuuint64_t strides[2] = {(cuuint64_t)N * 2, 64};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_atoms};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CF_REQUIRE(r == CUDA_SUCCESS, CF_ERR_CUDA, "cuTensorMapEncodeTiled (64B-swizzled feature map) failed with CUresult %d", (int)r);
+    return CF_OK;
+}
+
 // 3-D map over the level-0 volume [B][N][N], box {32 cols, 32 rows, 1}, 128B swizzle (store side)
 static int make_volume_tmap(CUtensorMap *m, float *base, int B, int N) {
     EncodeTiledFn fn = encode_fn();
@@ -1239,6 +1358,11 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     const int boxb = 128 * bk;                 // bytes per TMA box
     const int a_bytes = (BM / BC) * boxb;
     p.stage_bytes = a_bytes + p.n_boxes_b * boxb;
+    p.b_sw64 = 0;
+    if (f16 && p.b3d && !pair_req && !(flags & (1 << 17)) && p.BN_mma % 64 == 32 && p.BN % 32 == 0) {
+        p.b_sw64 = 1;
+        p.stage_bytes = a_bytes + (p.BN_mma / 32) * bk * 64;
+    }
     // two epilogue warps per TMEM lane quarter when the ring still gets >= 5 stages beside their 64 KB of buffers (fp16
     // operands); the deep pooling keeps per-thread row state and stays on one warp per quarter (flags bit7: force 1)
     // (measured slower again, also with the half-size fp16 stages: 396 against 359 us at 8 x 60x80 -- only on request)
@@ -1285,6 +1409,23 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // level-1 rows through shared memory into 64-byte runs (flags bit13: per-lane 16-byte stores): 64 x 24x32
     // 66.7 -> 60.8 us, 8 x 60x80 314 -> 309 us
     p.l1_staged = (p.R > 0 && p.w1 % 2 == 0 && !(flags & 8192)) ? 1 : 0;
+    // level 0 as one multi-atom box per lane quarter (kernel: qbox).  Needs whole tiles (h % R == 0), 32-column atoms that
+    // start on atom boundaries, whole lane quarters (N % 32 == 0) and the tile's level 0 (BN x 128 x 4 B) inside the shared
+    // memory left beside the operand ring -- for 160 columns that takes the 64-byte-swizzled fmap2 slice (b_sw64).  The
+    // level-1 scratch has no room then: level-1 rows leave as per-lane 16-byte stores.  Measured at 64 x 60x80 on two boxes:
+    // 2030 / 2090 us against 2047-2066 / 2128-2131 for the twenty single boxes (-1 to -2 %); default where the 64-byte-swizzled
+    // fmap2 slice is in use (the measured case), elsewhere on request (flags bit19); flags bit18 switches it off, bit17 b_sw64.
+    p.qbox = 0;
+    if (es == 2 && R > 0 && !(flags & (1 << 18)) && (p.b_sw64 || (flags & (1 << 19))) && h % R == 0 && N % 32 == 0 && p.BN % 32 == 0 && !p.lsu_stores && !pair &&
+        p.stages * p.stage_bytes + 4 * (p.BN / 32) * EPI_BUF_BYTES + 1024 + 256 <= SMEM_LIMIT) {
+        p.qbox = 1;
+        p.l1_staged = 0;
+        const int nch = p.BN / 32, ns = (R / 2) * (int)ceil_div(w, 32);
+        // a pooling strip costs a warp about twice a chunk (timeline): the second warp gets one strip more when their count is odd
+        p.qbox_h0 = (nch + 1) / 2 + ((ns & 1) ? 1 : 0);
+        if (p.qbox_h0 > nch) p.qbox_h0 = nch;
+        if ((flags >> 20) & 15) p.qbox_h0 = min(nch, ((flags >> 20) & 15) - 1);
+    }
     p.tiles_mp = (int)ceil_div(p.tiles_m, 2);
     p.b_half = (int)ceil_div(p.BN_mma / 2, 32);
     if (pair) {
@@ -1294,7 +1435,13 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         p.stages = (SMEM_LIMIT - smem_fixed(1)) / p.stage_bytes;
         if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     }
-    const int smem_bytes = p.stages * p.stage_bytes + smem_fixed(es);
+    p.epi_bytes = p.qbox ? 4 * (p.BN / 32) * EPI_BUF_BYTES : epi_bytes(es);
+    p.l1_scratch = 0;
+    if (es == 2 && !p.qbox && p.l1_staged && p.stages * p.stage_bytes + epi_bytes(2) + 8 * 2048 + 1024 + 256 <= SMEM_LIMIT) {
+        p.l1_scratch = epi_bytes(2);
+        p.epi_bytes += 8 * 2048;
+    }
+    const int smem_bytes = p.stages * p.stage_bytes + p.epi_bytes + 1024 + 256;
     CUtensorMap ta, tb, tcm;
     if (p.atoms3d) {
         if (int rc = make_fmap_tmap3(&ta, a, B, D, N, dt, bk, BM / BC)) return rc;
@@ -1302,11 +1449,15 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
         if (int rc = make_fmap_tmap(&ta, a, B, D, N, dt, bk)) return rc;
     }
     if (p.b3d) {
-        if (int rc = make_fmap_tmap3(&tb, bm, B, D, N, dt, bk, pair ? p.b_half : p.n_boxes_b)) return rc;
+        if (p.b_sw64) {
+            if (int rc = make_fmap_tmap3_sw64(&tb, bm, B, D, N, bk, p.BN_mma / 32)) return rc;
+        } else if (int rc = make_fmap_tmap3(&tb, bm, B, D, N, dt, bk, pair ? p.b_half : p.n_boxes_b)) return rc;
     } else {
         if (int rc = make_fmap_tmap(&tb, bm, B, D, N, dt, bk)) return rc;
     }
-    if (int rc = make_volume_tmap(&tcm, level0, B, N)) return rc;
+    if (p.qbox) {
+        if (int rc = make_volume_tmap_atoms(&tcm, level0, B, N, p.BN / 32)) return rc;
+    } else if (int rc = make_volume_tmap(&tcm, level0, B, N)) return rc;
 
     int dev = 0;
     CF_CUDA(cudaGetDevice(&dev));

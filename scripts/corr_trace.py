@@ -38,6 +38,9 @@ for c in ctas:
             break
         u = lambda v: (v - t0) / 1e3 if v else float('nan')
         land = " ".join(f"{u(v):6.2f}" for v in r[3:5])
-        w4 = f" || warp4 ready {u(r[5]):6.2f} l0 {u(r[6]):6.2f} done {u(r[7]):6.2f} | warp3 done {u(r[8]):6.2f} warp7 done {u(r[9]):6.2f}" if r[7] else ""
+        w4 = ""
+        if r[7]:
+            done = {0: r[14], 1: r[5], 2: r[6], 3: r[15], 4: r[7], 5: r[8], 6: r[9], 7: r[10]}
+            w4 = " || epilogue warps done " + " ".join(f"w{w}:{u(v):6.2f}" for w, v in done.items())
         print(f"  tile {k:2d}: loads {u(r[0]):6.2f}..{u(r[1]):6.2f} | acc free {u(r[2]):6.2f} landed [{land}] commit {u(r[11]):6.2f} "
               f"| epi ready {u(r[12]):6.2f} l0 issued {u(r[13]):6.2f} done {u(r[14]):6.2f}{w4}")

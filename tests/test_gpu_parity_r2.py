@@ -303,7 +303,7 @@ import torch
 import cistaflow_b200 as cf
 from cistaflow_b200 import synth
 dev = torch.device('cuda', 0)
-for (H, W, B) in ((480, 640, 2), (192, 256, 2)):
+for (H, W, B) in ((480, 640, 2), (192, 256, 2), (512, 512, 2)):
     f1, f2, _ = synth.corr_inputs(B, H, W, 6)
     a, b = torch.from_numpy(f1).to(dev), torch.from_numpy(f2).to(dev)
     ref = cf.build_pyramid(a, b, 4, precision='fp32')
@@ -313,6 +313,8 @@ for (H, W, B) in ((480, 640, 2), (192, 256, 2)):
         assert err <= 1e-3, (H, W, l, err)
 print('F16_OK')
 """
-    for flags in ("65536", "32", "128"):
+    # bit17: fmap2 slice in 128-byte-swizzled boxes again (and, with it, twenty single store boxes per tile); bit18: the 64-byte
+    # swizzled slice with single boxes; bit19: one store box per lane quarter also where the slice is 128-byte swizzled (192x256)
+    for flags in ("65536", "32", "128", str(1 << 17), str(1 << 18), str(1 << 19)):
         res = _run_with_env(code, {"CF_TC_FLAGS": flags})
         assert res.returncode == 0 and "F16_OK" in res.stdout, flags + res.stdout + res.stderr
