@@ -1359,7 +1359,9 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     const int a_bytes = (BM / BC) * boxb;
     p.stage_bytes = a_bytes + p.n_boxes_b * boxb;
     p.b_sw64 = 0;
-    if (f16 && p.b3d && !pair_req && !(flags & (1 << 17)) && p.BN_mma % 64 == 32 && p.BN % 32 == 0) {
+    // (the 128-byte-swizzled slice is one 3-D box only when tiles start on 64-column boundaries -- b3d; with 160-column tiles
+    //  it took three 2-D boxes per stage)
+    if (f16 && p.atoms3d && N % 32 == 0 && !pair_req && !(flags & (1 << 17)) && p.BN_mma % 64 == 32 && p.BN % 32 == 0) {
         p.b_sw64 = 1;
         p.stage_bytes = a_bytes + (p.BN_mma / 32) * bk * 64;
     }
@@ -1412,11 +1414,11 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // level 0 as one multi-atom box per lane quarter (kernel: qbox).  Needs whole tiles (h % R == 0), 32-column atoms that
     // start on atom boundaries, whole lane quarters (N % 32 == 0) and the tile's level 0 (BN x 128 x 4 B) inside the shared
     // memory left beside the operand ring -- for 160 columns that takes the 64-byte-swizzled fmap2 slice (b_sw64).  The
-    // level-1 scratch has no room then: level-1 rows leave as per-lane 16-byte stores.  Measured at 64 x 60x80 on two boxes:
-    // 2030 / 2090 us against 2047-2066 / 2128-2131 for the twenty single boxes (-1 to -2 %); default where the 64-byte-swizzled
-    // fmap2 slice is in use (the measured case), elsewhere on request (flags bit19); flags bit18 switches it off, bit17 b_sw64.
+    // level-1 scratch has no room then: level-1 rows leave as per-lane 16-byte stores.  Measured SLOWER at 64 x 60x80: 2476
+    // against 1985 us for the twenty single boxes on the same box (one buffer per lane quarter: every tile waits for its
+    // predecessor's box to leave, and two named barriers) -- only on request (flags bit19).  flags bit17 switches b_sw64 off.
     p.qbox = 0;
-    if (es == 2 && R > 0 && !(flags & (1 << 18)) && (p.b_sw64 || (flags & (1 << 19))) && h % R == 0 && N % 32 == 0 && p.BN % 32 == 0 && !p.lsu_stores && !pair &&
+    if (es == 2 && R > 0 && (flags & (1 << 19)) && h % R == 0 && N % 32 == 0 && p.BN % 32 == 0 && !p.lsu_stores && !pair &&
         p.stages * p.stage_bytes + 4 * (p.BN / 32) * EPI_BUF_BYTES + 1024 + 256 <= SMEM_LIMIT) {
         p.qbox = 1;
         p.l1_staged = 0;
@@ -1448,10 +1450,10 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     } else {
         if (int rc = make_fmap_tmap(&ta, a, B, D, N, dt, bk)) return rc;
     }
-    if (p.b3d) {
-        if (p.b_sw64) {
-            if (int rc = make_fmap_tmap3_sw64(&tb, bm, B, D, N, bk, p.BN_mma / 32)) return rc;
-        } else if (int rc = make_fmap_tmap3(&tb, bm, B, D, N, dt, bk, pair ? p.b_half : p.n_boxes_b)) return rc;
+    if (p.b_sw64) {
+        if (int rc = make_fmap_tmap3_sw64(&tb, bm, B, D, N, bk, p.BN_mma / 32)) return rc;
+    } else if (p.b3d) {
+        if (int rc = make_fmap_tmap3(&tb, bm, B, D, N, dt, bk, pair ? p.b_half : p.n_boxes_b)) return rc;
     } else {
         if (int rc = make_fmap_tmap(&tb, bm, B, D, N, dt, bk)) return rc;
     }

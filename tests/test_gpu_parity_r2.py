@@ -313,8 +313,8 @@ for (H, W, B) in ((480, 640, 2), (192, 256, 2), (512, 512, 2)):
         assert err <= 1e-3, (H, W, l, err)
 print('F16_OK')
 """
-    # bit17: fmap2 slice in 128-byte-swizzled boxes again (and, with it, twenty single store boxes per tile); bit18: the 64-byte
-    # swizzled slice with single boxes; bit19: one store box per lane quarter also where the slice is 128-byte swizzled (192x256)
-    for flags in ("65536", "32", "128", str(1 << 17), str(1 << 18), str(1 << 19)):
+    # bit17: the fmap2 slice in 128-byte-swizzled boxes (the default where tiles are 160 columns wide is the 64-byte swizzle);
+    # bit19: one level-0 store box per lane quarter and tile
+    for flags in ("65536", "32", "128", str(1 << 17), str(1 << 19)):
         res = _run_with_env(code, {"CF_TC_FLAGS": flags})
         assert res.returncode == 0 and "F16_OK" in res.stdout, flags + res.stdout + res.stderr
