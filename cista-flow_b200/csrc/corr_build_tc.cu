@@ -42,6 +42,13 @@
 // operands to TF32 (nearest) on their way into shared memory -- measured
 // identical to a cvt.rna.tf32.f32 pre-pass: bias -5e-7, max|err| 2.8e-4*max|ref|
 // -- so no extra pass over the feature maps and no workspace are needed.
+//
+// State at the end of round 2 (the notes below and at launch_tc() are the history that led here): on wide maps the default
+// is kind::f16 on fp16 operand copies, two 128-K-row stages per tile (fmap1 slice: one 128B-swizzled 3-D box; fmap2 slice:
+// one 64B-swizzled 3-D box of exactly BN columns), eight epilogue warps, levels 1 and 2 pooled in the epilogue.  At 64 x
+// 60x80 the GEMM kernel runs 3.4 us per 128x160 tile = 1.65 ms (ncu) and writes at 4.7-5.0 TB/s.  Its period is the SM's
+// TMA unit: four operand boxes (~0.32 us each) + twenty 4 KB store boxes (~0.12 us each) per tile queue in ONE unit
+// (scripts/experiments/write_probe.cu); the epilogue warps are busy ~3.0 us of it, the MMAs ~1.5 us.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
