@@ -1067,62 +1067,103 @@ fmap_to_half_kernel(const float *__restrict__ f1, const float *__restrict__ f2, 
 // 60x80 under ncu -- 15 % of the whole pyramid build.  Units are ordered by item and there are no more slices per item
 // than CTAs, so a CTA never waits for a slice that is queued behind its own (all CTAs of the launch fit on the chip at once).
 constexpr int CV_THREADS = 256, CV_F4 = 8;
-__global__ void __launch_bounds__(CV_THREADS)
+// (round 2, later: the loads of a CTA's NEXT slice are issued before it waits for the current item's arrival counter --
+//  without that all resident CTAs loaded, waited and stored in lockstep waves, reads and writes taking turns on the bus)
+__global__ void __launch_bounds__(CV_THREADS, 3)
 fmap_to_half_fused_kernel(const float *__restrict__ f1, const float *__restrict__ f2, int64_t per_item, int B, int parts,
                           unsigned *amax, int *arrived, __half *__restrict__ h1, __half *__restrict__ h2,
                           float *__restrict__ inv_scale) {
-    __shared__ float s_red[CV_THREADS / 32];
-    __shared__ float s_up;
+    __shared__ float s_red[2][CV_THREADS / 32];
+    __shared__ float s_up[2];
     const int64_t units = (int64_t)2 * B * parts, n4 = per_item >> 2;
-    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const int item = (int)(u / parts), part = (int)(u - (int64_t)item * parts);
-        const bool first = item < B;
-        const int64_t base = (int64_t)(first ? item : item - B) * per_item;
-        const float4 *s4 = reinterpret_cast<const float4 *>((first ? f1 : f2) + base);
-        uint2 *d4 = reinterpret_cast<uint2 *>((first ? h1 : h2) + base);
-        const int64_t i0 = (int64_t)part * (CV_THREADS * CV_F4) + threadIdx.x;
-        float4 v[CV_F4];
-        float m = 0.f;
+    struct Unit {
+        const float4 *s4;
+        uint2 *d4;
+        int64_t i0;
+        int item, part;
+    };
+    auto unit_of = [&](int64_t u) {
+        Unit t;
+        t.item = (int)(u / parts);
+        t.part = (int)(u - (int64_t)t.item * parts);
+        const bool first = t.item < B;
+        const int64_t base = (int64_t)(first ? t.item : t.item - B) * per_item;
+        t.s4 = reinterpret_cast<const float4 *>((first ? f1 : f2) + base);
+        t.d4 = reinterpret_cast<uint2 *>((first ? h1 : h2) + base);
+        t.i0 = (int64_t)t.part * (CV_THREADS * CV_F4) + threadIdx.x;
+        return t;
+    };
+    auto load = [&](const Unit &t, float4 (&v)[CV_F4]) {
 #pragma unroll
         for (int k = 0; k < CV_F4; ++k) {
-            const int64_t i = i0 + (int64_t)k * CV_THREADS;
-            v[k] = i < n4 ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            m = fmaxf(fmaxf(m, fmaxf(fabsf(v[k].x), fabsf(v[k].y))), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
+            const int64_t i = t.i0 + (int64_t)k * CV_THREADS;
+            v[k] = i < n4 ? __ldg(t.s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    // the slice's maximum -> the item's slot, arrival counted (thread 0 of the CTA); `slot` alternates between units
+    auto publish = [&](const Unit &t, const float4 (&v)[CV_F4], int slot) {
+        float m = 0.f;
+#pragma unroll
+        for (int k = 0; k < CV_F4; ++k)
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(v[k].x), fabsf(v[k].y))), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
         m = warp_max(m);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+        if ((threadIdx.x & 31) == 0) s_red[slot][threadIdx.x >> 5] = m;
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int k = 1; k < CV_THREADS / 32; ++k) m = fmaxf(m, s_red[k]);
-            if (m > 0.f) atomicMax(amax + item, __float_as_uint(fminf(m, 3.0e38f)));
+            for (int k = 1; k < CV_THREADS / 32; ++k) m = fmaxf(m, s_red[slot][k]);
+            if (m > 0.f) atomicMax(amax + t.item, __float_as_uint(fminf(m, 3.0e38f)));
             __threadfence();
-            atomicAdd(arrived + item, 1);
+            atomicAdd(arrived + t.item, 1);
+        }
+    };
+    // wait until every slice of the item has arrived, then scale and narrow out of registers
+    auto finish = [&](const Unit &t, const float4 (&v)[CV_F4], int slot) {
+        if (threadIdx.x == 0) {
             unsigned spins = 0;
-            while (*reinterpret_cast<volatile int *>(arrived + item) < parts) {
+            while (*reinterpret_cast<volatile int *>(arrived + t.item) < parts) {
                 __nanosleep(64);
                 if (++spins > (1u << 24)) __trap();
             }
             __threadfence();
-            const float mx = __uint_as_float(*reinterpret_cast<volatile unsigned *>(amax + item));
+            const float mx = __uint_as_float(*reinterpret_cast<volatile unsigned *>(amax + t.item));
             const int shift = mx > 0.f ? 13 - ilogbf(mx) : 0;
             const float up = ldexpf(1.f, shift > 126 ? 126 : shift);      // (a tiny maximum: clamp the exponent, still exact)
-            s_up = up;
-            if (part == 0) inv_scale[item] = 1.f / up;
+            s_up[slot] = up;
+            if (t.part == 0) inv_scale[t.item] = 1.f / up;
         }
         __syncthreads();
-        const float up = s_up;
+        const float up = s_up[slot];
 #pragma unroll
         for (int k = 0; k < CV_F4; ++k) {
-            const int64_t i = i0 + (int64_t)k * CV_THREADS;
+            const int64_t i = t.i0 + (int64_t)k * CV_THREADS;
             if (i < n4) {
                 const __half2 lo = __floats2half2_rn(v[k].x * up, v[k].y * up), hi = __floats2half2_rn(v[k].z * up, v[k].w * up);
                 uint2 o;
                 o.x = *reinterpret_cast<const unsigned *>(&lo);
                 o.y = *reinterpret_cast<const unsigned *>(&hi);
-                d4[i] = o;
+                t.d4[i] = o;
             }
         }
-        __syncthreads();   // s_red / s_up are reused by the next unit
+    };
+    // two register sets in turn: publish(cur) -> load(next) -> finish(cur)
+    float4 va[CV_F4], vb[CV_F4];
+    int64_t u = blockIdx.x;
+    if (u >= units) return;
+    Unit ta = unit_of(u), tb = ta;
+    load(ta, va);
+    for (;;) {
+        publish(ta, va, 0);
+        const bool more_b = u + gridDim.x < units;
+        if (more_b) { tb = unit_of(u + gridDim.x); load(tb, vb); }
+        finish(ta, va, 0);
+        if (!more_b) break;
+        u += gridDim.x;
+        publish(tb, vb, 1);
+        const bool more_a = u + gridDim.x < units;
+        if (more_a) { ta = unit_of(u + gridDim.x); load(ta, va); }
+        finish(tb, vb, 1);
+        if (!more_a) break;
+        u += gridDim.x;
     }
 }
 
