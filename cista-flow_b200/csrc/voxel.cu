@@ -102,6 +102,114 @@ voxel_scatter_atomic_kernel(const double *__restrict__ ev, const int64_t *__rest
     scatter_body(ev, off, B, nb, H, W, flavour, out, b_first, b_end, (int)blockIdx.x, (int)gridDim.x);
 }
 
+// ---- scatter + statistics in one pass (std normalisation) ------------------------------------------------
+// The statistics pass of the L2 path reads every grid of the chunk once more (~100 us of the 370 at 64 x 480x640) only to
+// form sum, sum of squares and the count of non-zero cells of the hot-pixel-filtered grid.  With RETURNING atomics they
+// telescope out of the scatter: an add takes a cell from `old` to `old + w` (the SM repeats the L2's round-to-nearest add;
+// no subnormals occur: |w| >= 2^-53), and f(new) - f(old), f(new)^2 - f(old)^2, [f(new) != 0] - [f(old) != 0] summed over all
+// adds of a cell give f(final), f(final)^2 and [f(final) != 0] (f = the hot-pixel filter; every difference and square is
+// exact in fp64).  Returning atomics retire at 87 G/s against 105 G/s for RED (profiles/r02/atomics_l2_probe.txt): the
+// scatter gets ~20 % slower and the statistics pass disappears.  Per thread fp64 accumulators, reduced per warp, three
+// atomics per warp and window into the window's first Partial (zeroed by the host); the normalise kernel is unchanged.
+// MEASURED (B200, same box, us per launch incl. normalisation): 64 x 480x640 419 against 367 with the separate statistics pass,
+// 8 x 480x640 50 against 44, 1 x 624x970 (1 M events) 56 against 30, 64 x 180x240 54.5 against 52.5 -- the returned values
+// make every add a round trip the thread waits for (8 in flight per thread at 2 CTAs per SM), far below the 87 G/s the
+// probe reached with nothing else to do.  Kept as an experiment (CF_VOXEL_FLAGS bit5), parity-tested; not the default.
+struct TelAcc {
+    double s, q;
+    long long n;
+    int b;
+};
+__device__ __forceinline__ void tel_flush(TelAcc &a, Partial *__restrict__ tel, int tel_stride) {
+    // lanes of a warp nearly always hold the same window: one reduced update then, else every lane for itself
+    const unsigned full = 0xffffffffu;
+    const int b0 = __shfl_sync(full, a.b, 0);
+    if (__all_sync(full, a.b == b0)) {
+        const double s = warp_sum(a.s), q = warp_sum(a.q);
+        const long long n = warp_sum(a.n);
+        if ((threadIdx.x & 31) == 0 && b0 >= 0 && (s != 0.0 || q != 0.0 || n != 0)) {
+            Partial *p = tel + (size_t)b0 * tel_stride;
+            atomicAdd(&p->sum, s);
+            atomicAdd(&p->sumsq, q);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&p->nnz), (unsigned long long)n);
+        }
+    } else if (a.b >= 0 && (a.s != 0.0 || a.q != 0.0 || a.n != 0)) {
+        Partial *p = tel + (size_t)a.b * tel_stride;
+        atomicAdd(&p->sum, a.s);
+        atomicAdd(&p->sumsq, a.q);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&p->nnz), (unsigned long long)a.n);
+    }
+    a.s = 0.0; a.q = 0.0; a.n = 0;
+}
+
+__global__ void __launch_bounds__(kScatterThreads)
+voxel_scatter_stats_kernel(const double *__restrict__ ev, const int64_t *__restrict__ off, int B, int nb, int H, int W,
+                           int flavour, float *__restrict__ out, int b_first, int b_end, float hot_thr,
+                           Partial *__restrict__ tel, int tel_stride) {
+    const int blk = (int)blockIdx.x, nblk = (int)gridDim.x;
+    const int64_t ev_first = __ldg(off + b_first), ev_end = __ldg(off + b_end);
+    const int64_t plane = (int64_t)H * W;
+    const int planes_per_bin = flavour == CF_FLAVOUR_POL ? 2 : 1;
+    constexpr int64_t kTileEvents = kScatterThreads * kScatterUnroll;
+    Window w;
+    w.b = -1;
+    TelAcc acc{0.0, 0.0, 0, -1};
+    for (int64_t tile = ev_first + (int64_t)blk * kTileEvents; tile < ev_end; tile += (int64_t)nblk * kTileEvents) {
+        Event e[kScatterUnroll];
+#pragma unroll
+        for (int k = 0; k < kScatterUnroll; ++k) {  // all loads in flight first
+            const int64_t i = tile + k * kScatterThreads + threadIdx.x;
+            if (i < ev_end) e[k] = load_event(ev, i);
+        }
+        // all adds of the tile in flight before the first returned value is used
+        float *cell[kScatterUnroll];
+        float wl[kScatterUnroll], wr[kScatterUnroll], ol[kScatterUnroll], orr[kScatterUnroll];
+        int wb[kScatterUnroll];
+        bool two[kScatterUnroll];
+#pragma unroll
+        for (int k = 0; k < kScatterUnroll; ++k) {
+            const int64_t i = tile + k * kScatterThreads + threadIdx.x;
+            cell[k] = nullptr;
+            two[k] = false;
+            wb[k] = -1;
+            if (i >= ev_end) continue;
+            locate_window(w, i, off, ev, B);
+            const Binned b = bin_event(e[k], w, nb, H, W, flavour);
+            if (!b.ok) continue;
+            if (flavour == CF_FLAVOUR_TORCH) {
+                weights_f32(b, wl[k], wr[k]);
+            } else {
+                double dl, dr;
+                weights_wide(b, flavour, dl, dr);
+                wl[k] = (float)dl;
+                wr[k] = (float)dr;
+            }
+            cell[k] = out + (((int64_t)w.b * nb + b.bin) * planes_per_bin + b.chan) * plane + (int64_t)b.y * W + b.x;
+            two[k] = b.bin + 1 < nb;
+            wb[k] = w.b;
+            ol[k] = atomicAdd(cell[k], wl[k]);
+            if (two[k]) orr[k] = atomicAdd(cell[k] + planes_per_bin * plane, wr[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kScatterUnroll; ++k) {
+            const bool live = cell[k] != nullptr;
+            // (warp-uniform test first: the flush is a warp collective)
+            if (__any_sync(0xffffffffu, live && wb[k] != acc.b && acc.b >= 0)) tel_flush(acc, tel, tel_stride);
+            if (!live) continue;
+            acc.b = wb[k];
+            auto take = [&](float old, float add) {
+                const float fo = hot_filter(old, hot_thr), fn = hot_filter(__fadd_rn(old, add), hot_thr);
+                acc.s += (double)fn - (double)fo;
+                acc.q += (double)fn * (double)fn - (double)fo * (double)fo;
+                acc.n += (long long)(fn != 0.f) - (long long)(fo != 0.f);
+            };
+            take(ol[k], wl[k]);
+            if (two[k]) take(orr[k], wr[k]);
+        }
+    }
+    tel_flush(acc, tel, tel_stride);
+}
+
 // ----------------------------------------- atomic mode, cluster (smem) path ---
 // fp32 add into the shared memory of CTA `rank` of this cluster (DSMEM), no return value
 __device__ __forceinline__ void red_add_cluster(float *local_ptr, unsigned rank, float v) {
@@ -741,7 +849,7 @@ static void stat_geometry(int B, int64_t cells, int &chunks, int64_t &chunk_len)
 }
 
 static int run_preprocess(const float *in, float *out, int B, int64_t cells, int preprocess, float hot_thr,
-                          void *ws, size_t ws_bytes, cudaStream_t stream) {
+                          void *ws, size_t ws_bytes, cudaStream_t stream, bool stats_done = false) {
     CF_REQUIRE(B <= 65535, CF_ERR_INVALID_ARG, "preprocess: B > 65535");
     CF_REQUIRE(ws && ws_bytes >= (size_t)B * kMaxChunks * sizeof(Partial), CF_ERR_WORKSPACE,
                "preprocess: workspace too small (%zu < %zu)", ws_bytes, (size_t)B * kMaxChunks * sizeof(Partial));
@@ -751,8 +859,10 @@ static int run_preprocess(const float *in, float *out, int B, int64_t cells, int
     stat_geometry(B, cells, chunks, chunk_len);
     Partial *partials = reinterpret_cast<Partial *>(ws);
     dim3 grid(chunks, B);
-    voxel_stats_kernel<<<grid, kStatThreads, 0, stream>>>(in, cells, chunk_len, hot_thr, partials, chunks);
-    CF_LAUNCH_CHECK("voxel_stats_kernel");
+    if (!stats_done) {   // (else the scatter left each window's totals in its first Partial, the others zero)
+        voxel_stats_kernel<<<grid, kStatThreads, 0, stream>>>(in, cells, chunk_len, hot_thr, partials, chunks);
+        CF_LAUNCH_CHECK("voxel_stats_kernel");
+    }
     voxel_normalise_kernel<<<grid, kStatThreads, 0, stream>>>(in, out, cells, chunk_len, hot_thr, preprocess, partials, chunks);
     CF_LAUNCH_CHECK("voxel_normalise_kernel");
     return CF_OK;
@@ -791,7 +901,7 @@ static bool use_tiled(int64_t, int, int64_t) {
     return (voxel_flags() & 8) != 0;              // experiments: CF_VOXEL_FLAGS=8 forces the tiled path
 }
 
-// CF_VOXEL_FLAGS (debug / experiments): bit4 = pipelined launches (four stages of four chunks per launch), bit3 = force the tiled path,
+// CF_VOXEL_FLAGS (debug / experiments): bit5 = statistics telescoped out of a returning-atomics scatter, bit4 = pipelined launches (four stages of four chunks per launch), bit3 = force the tiled path,
 // bit2 = force the L2-atomic path, bit1 = use the cluster / DSMEM-atomics path, bit0 = do not chunk
 static int voxel_flags() {
     static int flags = -1;
@@ -1001,6 +1111,8 @@ extern "C" int cf_voxel_bin(const double *events, const int64_t *offsets, int64_
             }
             return CF_OK;
         }
+        const bool telescope = preprocess == CF_PRE_STD && (voxel_flags() & 32) && ws != nullptr &&
+                               ws_bytes >= (size_t)B * kMaxChunks * sizeof(Partial);
         for (int b0 = 0; b0 < B; b0 += chunk) {
             const int nbat = B - b0 < chunk ? B - b0 : chunk;
             float *o = out + (size_t)b0 * cells;
@@ -1012,14 +1124,27 @@ extern "C" int cf_voxel_bin(const double *events, const int64_t *offsets, int64_
                 const int64_t cap = (int64_t)sm_count() * 8;
                 if (blocks > cap) blocks = cap;
                 if (blocks < 1) blocks = 1;
-                voxel_scatter_atomic_kernel<<<(unsigned)blocks, kScatterThreads, 0, stream>>>(
-                    events, offsets, B, nb, H, W, flavour, out, b0, b0 + nbat);
-                CF_LAUNCH_CHECK("voxel_scatter_atomic_kernel");
+                if (telescope) {
+                    // statistics out of the scatter's returned values (std mode; experiment, CF_VOXEL_FLAGS bit5 -- measured slower)
+                    Partial *tel = reinterpret_cast<Partial *>(reinterpret_cast<char *>(ws) + (size_t)b0 * kMaxChunks * sizeof(Partial));
+                    int tchunks;
+                    int64_t tlen;
+                    stat_geometry(nbat, cells, tchunks, tlen);
+                    CF_CUDA(cudaMemsetAsync(tel, 0, sizeof(Partial) * (size_t)nbat * tchunks, stream));
+                    voxel_scatter_stats_kernel<<<(unsigned)blocks, kScatterThreads, 0, stream>>>(
+                        events, offsets, B, nb, H, W, flavour, out, b0, b0 + nbat, hot_thr, tel - (size_t)b0 * tchunks, tchunks);
+                    CF_LAUNCH_CHECK("voxel_scatter_stats_kernel");
+                } else {
+                    voxel_scatter_atomic_kernel<<<(unsigned)blocks, kScatterThreads, 0, stream>>>(
+                        events, offsets, B, nb, H, W, flavour, out, b0, b0 + nbat);
+                    CF_LAUNCH_CHECK("voxel_scatter_atomic_kernel");
+                }
             }
             if (preprocess != CF_PRE_NONE) {
                 if (int rc = run_preprocess(o, o, nbat, cells, preprocess, hot_thr,
                                             reinterpret_cast<char *>(ws) + (size_t)b0 * kMaxChunks * sizeof(Partial),
-                                            ws_bytes - (size_t)b0 * kMaxChunks * sizeof(Partial), stream)) return rc;
+                                            ws_bytes - (size_t)b0 * kMaxChunks * sizeof(Partial), stream,
+                                            /*stats_done=*/telescope && total > 0)) return rc;
             }
         }
         return CF_OK;

@@ -278,9 +278,10 @@ for (h, w, n, B, mb) in ((60, 80, 9000, 7, '1'), (180, 240, 15000, 5, '96')):
     ev, off = synth.event_windows(B, n, h, w, seed=3)
     e, o = torch.from_numpy(ev).to(dev), torch.from_numpy(off).to(dev)
     raw = cf.events_to_voxel_grid_batched(e, o, 5, w, h, flavour='numpy', mode='atomic_l2').cpu().numpy()
-    assert _lib.load().cf_last_kernel().decode() == 'voxel_pipeline_kernel', _lib.load().cf_last_kernel()
+    assert _lib.load().cf_last_kernel().decode() == EXPECT_RAW, _lib.load().cf_last_kernel()
     fused = cf.events_to_voxel_grid_batched(e, o, 5, w, h, normalize='std', filter_hot_pixel=True, flavour='numpy',
                                             mode='atomic_l2').cpu().numpy()
+    assert _lib.load().cf_last_kernel().decode() == EXPECT_FUSED, _lib.load().cf_last_kernel()
     for b in range(B):
         ref = explicit.voxel_grid_sequential(ev[off[b]:off[b + 1]], 5, w, h, explicit.FLAVOUR_NUMPY)
         pos = ev[off[b]:off[b + 1]].copy(); pos[:, 3] = 1.0
@@ -291,7 +292,12 @@ print('PIPE_OK')
 """
     # a 1 MB chunk budget forces several chunks (stages of different chunks in one launch) at the small shape
     for mb in ("1", "96"):
-        res = _run_with_env(code, {"CF_VOXEL_FLAGS": "16", "CF_VOXEL_CHUNK_MB": mb})
+        res = _run_with_env("EXPECT_RAW = EXPECT_FUSED = 'voxel_pipeline_kernel'\n" + code, {"CF_VOXEL_FLAGS": "16", "CF_VOXEL_CHUNK_MB": mb})
+        assert res.returncode == 0 and "PIPE_OK" in res.stdout, res.stdout + res.stderr
+    # bit5: statistics telescoped out of a scatter with returning atomics (no statistics pass)
+    for mb in ("1", "96"):
+        res = _run_with_env("EXPECT_RAW, EXPECT_FUSED = 'voxel_scatter_atomic_kernel', 'voxel_normalise_kernel'\n" + code,
+                            {"CF_VOXEL_FLAGS": "32", "CF_VOXEL_CHUNK_MB": mb})
         assert res.returncode == 0 and "PIPE_OK" in res.stdout, res.stdout + res.stderr
 
 
