@@ -1458,13 +1458,17 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // buffers in flight and waits for its bulk stores once per strip.  Removed again; the two-phase epilogue stays.
     // level-1 rows through shared memory into 64-byte runs (flags bit13: per-lane 16-byte stores): 64 x 24x32
     // 66.7 -> 60.8 us, 8 x 60x80 314 -> 309 us
-    p.l1_staged = (p.R > 0 && p.w1 % 2 == 0 && !(flags & 8192)) ? 1 : 0;
+    p.l1_staged = (p.R > 0 && p.w1 % 2 == 0 && !(flags & 8192) && !(flags & (1 << 24))) ? 1 : 0;   // (bit24: off, without bit13's ablation side effect)
     // level 0 as one multi-atom box per lane quarter (kernel: qbox).  Needs whole tiles (h % R == 0), 32-column atoms that
     // start on atom boundaries, whole lane quarters (N % 32 == 0) and the tile's level 0 (BN x 128 x 4 B) inside the shared
     // memory left beside the operand ring -- for 160 columns that takes the 64-byte-swizzled fmap2 slice (b_sw64).  The
     // level-1 scratch has no room then: level-1 rows leave as per-lane 16-byte stores.  Measured SLOWER at 64 x 60x80: 2476
     // against 1985 us for the twenty single boxes on the same box (one buffer per lane quarter: every tile waits for its
     // predecessor's box to leave, and two named barriers) -- only on request (flags bit19).  flags bit17 switches b_sw64 off.
+    // Most of that loss is the level-1 rows: per-lane 16-byte stores alone (flags bit24, single boxes) cost 2485 against 2015 us
+    // at this shape.  A variant with one {32 x 32 x 3 | 2} box per WARP (no barrier, 8 stores per tile; write_probe: 5.8 against
+    // 4.9 TB/s for the stores alone, 4.3 against 3.7 with the operand loads) measured 2630 us with the same level-1 stores,
+    // i.e. still behind the single boxes -- removed again.
     p.qbox = 0;
     if (es == 2 && R > 0 && (flags & (1 << 19)) && h % R == 0 && N % 32 == 0 && p.BN % 32 == 0 && !p.lsu_stores && !pair &&
         p.stages * p.stage_bytes + 4 * (p.BN / 32) * EPI_BUF_BYTES + 1024 + 256 <= SMEM_LIMIT) {

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128) row_full_kernel(float *dst, int B, int N,
 // Tile order = the kernel's (nb fastest, interleaved over the grid) or, with A_RES, runs of 15 consecutive nb per CTA.
 template <int STORE, bool A_RES, int LOADS>
 __global__ void __launch_bounds__(320) move_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_c,
-            const __grid_constant__ CUtensorMap tmap_c2, const __grid_constant__ CUtensorMap tmap_c5,
+            const __grid_constant__ CUtensorMap tmap_c2, const __grid_constant__ CUtensorMap tmap_c5, const __grid_constant__ CUtensorMap tmap_c3,
                                                    float *dst, const void *dst_aux, int B, int N, int BN) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full[2];
@@ -285,6 +285,26 @@ __global__ void __launch_bounds__(320) move_kernel(const __grid_constant__ CUten
             }
         }
         bulk_wait<0>();
+    } else if (STORE == 5) {
+        // one box per WARP and tile: the first warp of a lane quarter stores chunks 0-2 as {32, 32, 3}, the second chunks 3-4 as
+        // {32, 32, 2}; one buffer per warp (12 / 8 KB), no barrier between the warps
+        uint8_t *mine = epi + ((warp & 3) * 20480 + (warp >> 2) * 12288) % 49152;   // (probe: buffers may overlap, contents do not matter)
+        const int q = warp & 3, half = warp >> 2;
+        if (lane != 0) return;
+        for (long long k = 0; tile_at(k) < total; ++k) {
+            const long long tile = tile_at(k);
+            const int nb = (int)(tile % tiles_n);
+            const long long t = tile / tiles_n;
+            const int mb = (int)(t % tiles_m), b = (int)(t / tiles_m);
+            const int row0 = mb * 128 + q * 32;
+            bulk_wait_read<0>();
+            if (row0 < N) {
+                if (half == 0) box_store_3d(&tmap_c3, mine, 0, b * N + row0, (nb * BN) / 32);
+                else box_store_3d(&tmap_c2, mine, 0, b * N + row0, (nb * BN) / 32 + 3);
+            }
+            bulk_commit();
+        }
+        bulk_wait<0>();
     } else if (STORE == 4) {
         // one 5-atom box {32, 32, 5} = the whole 32 x 160 slab of a lane quarter per instruction (probe only: 20 KB staging each)
         if (warp >= 4 || lane != 0) return;
@@ -403,7 +423,7 @@ int main(int argc, char **argv) {
         const int stage = (2 + 3) * 64 * 128 * 2;
         const int sm_box = 2 * stage + 8 * 2 * 4096, sm_row = 2 * stage + 32 * (BN * 4 + 16);
         printf("loads + stores together (per tile: 2 stages of 80 KB in, 80 KB out); sm_box %d sm_row %d\n", sm_box, sm_row);
-        CUtensorMap mc2, mc5;
+        CUtensorMap mc2, mc5, mc3;
         {
             cuuint64_t cd[3] = {32, (cuuint64_t)B * N, (cuuint64_t)(N / 32)};
             cuuint64_t cs[2] = {(cuuint64_t)N * 4, 128};
@@ -412,11 +432,15 @@ int main(int argc, char **argv) {
                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             CUresult rb = encode_fn()(&mc5, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, buf, cd, cs, b5, e3, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            cuuint32_t b3[3] = {32, 32, 3};
+            CUresult rc3 = encode_fn()(&mc3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, buf, cd, cs, b3, e3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rc3 != CUDA_SUCCESS) { printf("volume 3-atom encode failed (%d)\n", (int)rc3); return 1; }
             if (ra != CUDA_SUCCESS || rb != CUDA_SUCCESS) { printf("volume 3-D encode failed (%d %d)\n", (int)ra, (int)rb); return 1; }
         }
 #define RUNMOVE(NAME, ST, AR, LD, SM)                                                                                        \
         CK(cudaFuncSetAttribute(move_kernel<ST, AR, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));                   \
-        timed(NAME, (double)bytes, [&] { move_kernel<ST, AR, LD><<<148, (LD == 2 ? 320 : 288), SM>>>(mfa, mf, m, mc2, mc5, (float *)buf, fm, B, N, BN); });
+        timed(NAME, (double)bytes, [&] { move_kernel<ST, AR, LD><<<148, (LD == 2 ? 320 : 288), SM>>>(mfa, mf, m, mc2, mc5, mc3, (float *)buf, fm, B, N, BN); });
         RUNMOVE("loads only", 0, false, 1, sm_box)
         RUNMOVE("loads only, A resident", 0, true, 1, sm_box)
         RUNMOVE("box stores only", 1, false, 0, sm_box)
@@ -426,6 +450,8 @@ int main(int argc, char **argv) {
         RUNMOVE("LSU loads + box stores", 1, false, 2, sm_box)
         RUNMOVE("2-atom boxes only", 3, false, 0, sm_box)
         RUNMOVE("loads + 2-atom boxes", 3, false, 1, sm_box)
+        RUNMOVE("per-warp 3|2-atom only", 5, false, 0, sm_box)
+        RUNMOVE("loads + per-warp 3|2", 5, false, 1, sm_box)
         RUNMOVE("5-atom boxes only", 4, false, 0, sm_box)
         RUNMOVE("loads + 5-atom boxes", 4, false, 1, sm_box)
         if (sm_row <= 227 * 1024) {
