@@ -93,6 +93,10 @@ struct Params {
     int n_boxes_b; // TMA boxes per stage for the B operand
     int R;         // target rows per tile when pooling is fused (0 = not fused)
     int tiles_m, tiles_n, total_tiles;
+    int tiles_nv;  // target tiles per query block in the tile index (= tiles_n, rounded up to 4 with quad3: indices with
+                   // nb >= tiles_n are skipped by every role)
+    int quad3;     // 1 (with pair2): a CTA takes the tiles of FOUR consecutive target-row pairs back to back and the epilogue pools
+                   // level 3 from two level-2 rows (the first one parked in free TMEM columns, like pair2's level-1 row)
     int tiles_mp;  // pair kernel: pairs of query tiles per batch item (= ceil(tiles_m / 2)); total_tiles counts pairs
     int stages;      // shared-memory ring depth
     int stage_bytes; // A_BYTES + n_boxes_b * BOX_BYTES
@@ -299,6 +303,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -367,8 +381,8 @@ __device__ __forceinline__ void stamp(int slot) {
 #endif
 
 __device__ __forceinline__ void decode_tile(const Params &p, int tile, int &b, int &mb, int &nb) {
-    nb = tile % p.tiles_n;
-    const int t = tile / p.tiles_n;
+    nb = tile % p.tiles_nv;
+    const int t = tile / p.tiles_nv;
     mb = t % p.tiles_m;
     b = t / p.tiles_m;
 }
@@ -455,23 +469,23 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int first_tile = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
     // the s-th tile of this CTA: tile indices have the target-row pair nb fastest, so with pair2 a CTA takes the two tiles
     // 2u, 2u+1 of unit u back to back (same batch item, same query rows, target rows 4u' .. 4u'+3)
-    const int GS = p.pair2 ? 2 : 1, gs_shift = p.pair2 ? 1 : 0;
+    const int GS = p.quad3 ? 4 : (p.pair2 ? 2 : 1), gs_shift = p.quad3 ? 2 : (p.pair2 ? 1 : 0);
     auto tile_of = [&](int sq) { return ((first_tile + (sq >> gs_shift) * tile_step) << gs_shift) + (sq & (GS - 1)); };
     // (b, mb, nb) of the next tile of this CTA without integer divisions (three of them per tile, twice with the look-ahead
     // of the fp16 epilogue, were ~0.5 us of every tile's serial chain): the step from the last tile of a group to the first
     // of the next is a constant, decomposed once
     const int jump = GS * tile_step - (GS - 1);
-    const int jump_n = jump % p.tiles_n, jump_m = (jump / p.tiles_n) % p.tiles_m, jump_b = (jump / p.tiles_n) / p.tiles_m;
+    const int jump_n = jump % p.tiles_nv, jump_m = (jump / p.tiles_nv) % p.tiles_m, jump_b = (jump / p.tiles_nv) / p.tiles_m;
     auto advance = [&](int sq, int &tile, int &b, int &mb, int &nb) {   // tile of sequence number sq -> sq + 1   (CL == 1)
-        if (GS == 2 && !(sq & 1)) {   // second tile of a pair: the next target-row pair (tiles_n is even with pair2)
+        if ((sq & (GS - 1)) != GS - 1) {   // next tile of the group: the next target-row pair (tiles_nv is a multiple of GS)
             ++tile;
             ++nb;
             return;
         }
         tile += jump;
         nb += jump_n;
-        int c = nb >= p.tiles_n ? 1 : 0;
-        nb -= c ? p.tiles_n : 0;
+        int c = nb >= p.tiles_nv ? 1 : 0;
+        nb -= c ? p.tiles_nv : 0;
         mb += jump_m + c;
         c = mb >= p.tiles_m ? 1 : 0;
         mb -= c ? p.tiles_m : 0;
@@ -518,6 +532,10 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (CL == 1 && tile < p.total_tiles) decode_tile(p, tile, b, mb, nb);
             for (; tile < p.total_tiles; ++tile_no) {
                 if (CL == 2) decode_pair_tile(p, tile, rank, b, mb, nb);
+                if (CL == 1 && nb >= p.tiles_n) {   // (quad3: padding index, no such tile)
+                    advance(tile_no, tile, b, mb, nb);
+                    continue;
+                }
                 const int i0 = mb * BM, j0 = nb * p.BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -601,7 +619,14 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t kstep_b = sw64 ? (1024u >> 4) : (uint32_t)(KSTEP >> 4);
             const uint32_t smem_base = smem_u32(smem);
             int tile_no = 0;
+            int wb_ = 0, wmb_ = 0, wnb_ = 0, wtile_ = tile_of(0);          // (b, mb, nb) carried only to skip quad3's padding indices
+            if (CL == 1 && wtile_ < p.total_tiles) decode_tile(p, wtile_, wb_, wmb_, wnb_);
             for (int tile = tile_of(0); tile < p.total_tiles; tile = tile_of(++tile_no)) {
+                if (CL == 1) {
+                    const bool skip = wnb_ >= p.tiles_n;
+                    advance(tile_no, wtile_, wb_, wmb_, wnb_);
+                    if (skip) continue;
+                }
                 mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
                 tc_fence_after();
                 if (lane == 0) TC_TRACE(tile_no, 2);
@@ -686,6 +711,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 inv_a = __ldg(p.inv_scale + b_nx);
                 inv_b = __ldg(p.inv_scale + p.B + b_nx);
             }
+            if (CL == 1 && nb >= p.tiles_n) continue;   // (quad3: padding index -- after the look-ahead, which every index owes its successor)
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             if (tile_no == 0 && threadIdx.x == 0) stamp(20);
@@ -904,6 +930,31 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                     for (int q = 0; q < 2; ++q)
                                         if (4 * q < n2)
                                             *(reinterpret_cast<float4 *>(d2) + q) = make_float4(l2v[4 * q], l2v[4 * q + 1], l2v[4 * q + 2], l2v[4 * q + 3]);
+                                }
+                                if (p.quad3) {
+                                    // level 3 across the quad: the second tile parks this level-2 strip behind the level-1
+                                    // park (16 columns per strip there, 8 per strip here), the fourth pools 4 level-3 values per query and strip
+                                    const uint32_t park2 = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(p.BN_mma + 16 * ((p.w + 31) >> 5)) + (uint32_t)(xc >> 2);
+                                    if ((nb & 3) == 1) {
+                                        uint32_t ov[8];
+#pragma unroll
+                                        for (int q = 0; q < 8; ++q) ov[q] = __float_as_uint(l2v[q]);
+                                        tmem_st8(park2, ov);
+                                    } else {
+                                        uint32_t qv[8];
+                                        tmem_ld8(park2, qv);
+                                        const int r3g = nb >> 2, n3 = min(4, p.w3 - (xc >> 3));
+                                        if (row_ok && r3g < p.h3 && !(p.ablate & 1)) {
+                                            float *d3 = p.l3 + (((size_t)b * p.N + i) * p.h3 + r3g) * p.w3 + (xc >> 3);
+#pragma unroll
+                                            for (int q = 0; q < 4; ++q) {
+                                                float s3 = __uint_as_float(qv[2 * q]) + __uint_as_float(qv[2 * q + 1]);
+                                                s3 += l2v[2 * q];
+                                                s3 += l2v[2 * q + 1];
+                                                if (q < n3) d3[q] = s3 * 0.25f;
+                                            }
+                                        }
+                                    }
                                 }
                             }
                         }
@@ -1379,7 +1430,16 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     if (R == 2 && p.deep == 0 && !(flags & 8) && !(flags & 64) && level2 != nullptr && aligned16(level2) && h % 4 == 0 && w % 16 == 0 &&
         (int)align_up(R * w, 16) + w / 2 <= MAX_BN)
         p.pair2 = 1;
-    *fused_levels = R > 0 ? 1 + (p.pair2 ? 1 : p.deep) : 0;
+    // ... and level 3 out of quads of tiles (kernel: quad3): needs level-2 rows that pool inside a 32-column strip (w % 16 == 0
+    // gives 4 or 8 level-2 values per strip) and w2 more free TMEM columns; h / 8 level-3 rows (a last half quad only parks)
+    // MEASURED SLOWER (64 x 60x80: 2571 against 2007-2026 us, 8 x 60x80: 293 against 255): it saves the 89 us pooling kernel, but a
+    // lane's four level-3 values are 16 bytes of a 280-byte per-query map -- 32 scattered partial-sector writes per store
+    // instruction where the pooling kernel writes level 3 as one dense stream.  Parity-tested, on request only (flags bit25).
+    p.quad3 = 0;
+    if (p.pair2 && level3 != nullptr && (flags & (1 << 25)) && h >= 8 && w >= 8 &&
+        (int)align_up(R * w, 16) + 24 * (int)ceil_div(w, 32) <= MAX_BN)
+        p.quad3 = 1;
+    *fused_levels = R > 0 ? 1 + (p.quad3 ? 2 : (p.pair2 ? 1 : p.deep)) : 0;
     p.stream_l0 = (int64_t)B * N * N * 4 > (64ll << 20);
     if (R > 0) {
         p.R = R;
@@ -1393,7 +1453,8 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     p.BN_mma = (int)align_up(p.BN, 16);
     p.n_boxes_b = (int)ceil_div(p.BN_mma, BC);
     p.tiles_m = (int)ceil_div(N, BM);
-    const int64_t total = (int64_t)B * p.tiles_m * p.tiles_n;
+    p.tiles_nv = p.quad3 ? (int)align_up(p.tiles_n, 4) : p.tiles_n;
+    const int64_t total = (int64_t)B * p.tiles_m * p.tiles_nv;
     CF_REQUIRE(total < (1ll << 31), CF_ERR_INVALID_ARG, "cf_corr_build: too many tiles");
     p.total_tiles = (int)total;
 
