@@ -101,6 +101,8 @@ struct Params {
     int stages;      // shared-memory ring depth
     int stage_bytes; // A_BYTES + n_boxes_b * BOX_BYTES
     int qbox_h0;     // qbox: level-0 chunks of the first warp of a lane quarter
+    int frag_stores; // 1: level 0 leaves straight from registers in the tcgen05.ld.16x256b fragment layout (32-byte runs, no shared
+                     // memory, no TMA store) -- see launch_tc()
     int qbox;        // 1 (two epilogue warps per lane quarter): level 0 leaves as ONE {32 cols, 32 rows, BN/32 atoms} box per lane
                      // quarter and tile (tmap_c is then that 3-D map over {32, B*N rows, N/32 atoms}) -- see launch_tc()
     int epi_bytes;   // bytes of epilogue buffers between the operand ring and the barriers
@@ -302,6 +304,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 16 lanes x 32 columns in the 16x256b fragment layout: thread t <- for every 8-column block j: (lane t/4, columns 8j + 2(t%4), +1) in
+// v[4j], v[4j+1] and (lane t/4 + 8, same columns) in v[4j+2], v[4j+3] -- four threads hold one 32-byte run of a row
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -730,7 +742,33 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // ---- level 0: TMEM -> registers (x scale) -> swizzled smem box -> TMA bulk store.
             // A warp-wide st.global of this fragment would touch 32 different rows per instruction
             // (measured: 18k cycles per tile); the TMA writes whole 128-byte lines instead.
-            if (p.qbox && !(p.ablate & 64)) {
+            if (p.frag_stores && bn_valid == p.BN && !(p.ablate & 64)) {
+                // ---- level 0 straight from registers: the 16x256b fragment gives four neighbouring threads one 32-byte run of
+                // a row, so a warp-wide st.global.v2 writes eight whole sectors -- no staging in shared memory, no fence, and
+                // no store box in the TMA unit, which then carries only the operand stages (write_probe: loads + these stores
+                // 4.1 TB/s against 3.6 with the twenty boxes).  MEASURED SLOWER in the kernel (64 x 60x80, same box: 2565-2600 against
+                // 2222-2227 us): the LSU already carries the level-1 and level-2 rows.  Experiment, flags bit26, parity-tested.
+                for (int ci = half; ci < p.BN / 32; ci += EPI_SPLIT) {
+#pragma unroll
+                    for (int hr = 0; hr < 2; ++hr) {
+                        uint32_t v[16];
+                        tmem_ld_16x256b_x4(tmem_base + ((uint32_t)(32 * quarter + 16 * hr) << 16) + (uint32_t)acc * MAX_BN + (uint32_t)(32 * ci), v);
+                        tmem_ld_wait();
+                        const int r = mb * BM + 32 * quarter + 16 * hr + (lane >> 2);
+                        float *dst = p.l0 + ((size_t)b * p.N + r) * p.N + j0 + 32 * ci + 2 * (lane & 3);
+                        if (!(p.ablate & 1)) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 lo = make_float2(__uint_as_float(v[4 * j]) * scale, __uint_as_float(v[4 * j + 1]) * scale);
+                                const float2 hi = make_float2(__uint_as_float(v[4 * j + 2]) * scale, __uint_as_float(v[4 * j + 3]) * scale);
+                                float2 *d0 = reinterpret_cast<float2 *>(dst + 8 * j), *d1 = reinterpret_cast<float2 *>(dst + (size_t)8 * p.N + 8 * j);
+                                if (r < p.N) { if (p.stream_l0) __stcs(d0, lo); else *d0 = lo; }
+                                if (r + 8 < p.N) { if (p.stream_l0) __stcs(d1, hi); else *d1 = hi; }
+                            }
+                        }
+                    }
+                }
+            } else if (p.qbox && !(p.ablate & 64)) {
                 // ---- level 0, one box per lane quarter: the SM's TMA unit carries the operand stages and the volume's stores
                 // and is ~90 % busy (profiles/r02/write_probe.txt, corr_trace_f16_8x60x80.txt); twenty {32 x 32} boxes per tile cost
                 // it 2.4 us, four {32 x 32 x 5} boxes 1.5 us.  The two warps of the quarter stage their chunks (same swizzled
@@ -1530,6 +1568,7 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // at this shape.  A variant with one {32 x 32 x 3 | 2} box per WARP (no barrier, 8 stores per tile; write_probe: 5.8 against
     // 4.9 TB/s for the stores alone, 4.3 against 3.7 with the operand loads) measured 2630 us with the same level-1 stores,
     // i.e. still behind the single boxes -- removed again.
+    p.frag_stores = (R > 0 && (flags & (1 << 26)) && h % R == 0 && N % 8 == 0 && p.BN % 32 == 0 && !pair) ? 1 : 0;
     p.qbox = 0;
     if (es == 2 && R > 0 && (flags & (1 << 19)) && h % R == 0 && N % 32 == 0 && p.BN % 32 == 0 && !p.lsu_stores && !pair &&
         p.stages * p.stage_bytes + 4 * (p.BN / 32) * EPI_BUF_BYTES + 1024 + 256 <= SMEM_LIMIT) {

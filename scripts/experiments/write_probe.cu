@@ -305,6 +305,27 @@ __global__ void __launch_bounds__(320) move_kernel(const __grid_constant__ CUten
             bulk_commit();
         }
         bulk_wait<0>();
+    } else if (STORE == 6) {
+        // level 0 straight from registers in the tcgen05.ld.16x256b fragment layout: thread t holds (row t/4, columns 2(t%4), +1)
+        // and (row t/4 + 8, same columns) of every 8-column block -- four threads cover one 32-byte sector, a warp-wide
+        // st.global.v2 eight rows x 32 B.  No shared memory, no TMA store.  Warp w: rows 32 (w & 3) .. +31, column half w >> 2.
+        const int q = warp & 3, half = warp >> 2;
+        const int c_lo = half ? 96 : 0, c_hi = half ? BN : 96;
+        const float2 v = make_float2(1.f, 2.f);
+        for (long long k = 0; tile_at(k) < total; ++k) {
+            const long long tile = tile_at(k);
+            const int nb = (int)(tile % tiles_n);
+            const long long t = tile / tiles_n;
+            const int mb = (int)(t % tiles_m), b = (int)(t / tiles_m);
+            const int row0 = mb * 128 + q * 32 + (lane >> 2);
+            float *base = dst + ((size_t)b * N + row0) * N + nb * BN + 2 * (lane & 3);
+#pragma unroll 1
+            for (int c = c_lo; c < c_hi; c += 8) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (row0 + 8 * r < N) *reinterpret_cast<float2 *>(base + (size_t)(8 * r) * N + c) = v;
+            }
+        }
     } else if (STORE == 4) {
         // one 5-atom box {32, 32, 5} = the whole 32 x 160 slab of a lane quarter per instruction (probe only: 20 KB staging each)
         if (warp >= 4 || lane != 0) return;
@@ -450,6 +471,8 @@ int main(int argc, char **argv) {
         RUNMOVE("LSU loads + box stores", 1, false, 2, sm_box)
         RUNMOVE("2-atom boxes only", 3, false, 0, sm_box)
         RUNMOVE("loads + 2-atom boxes", 3, false, 1, sm_box)
+        RUNMOVE("fragment st.v2 only", 6, false, 0, sm_box)
+        RUNMOVE("loads + fragment st.v2", 6, false, 1, sm_box)
         RUNMOVE("per-warp 3|2-atom only", 5, false, 0, sm_box)
         RUNMOVE("loads + per-warp 3|2", 5, false, 1, sm_box)
         RUNMOVE("5-atom boxes only", 4, false, 0, sm_box)

@@ -322,6 +322,7 @@ print('F16_OK')
     # bit17: the fmap2 slice in 128-byte-swizzled boxes (the default where tiles are 160 columns wide is the 64-byte swizzle);
     # bit19: one level-0 store box per lane quarter and tile
     # bit25: level 3 pooled in the epilogue out of quads of tiles (tile indices padded to groups of four)
-    for flags in ("65536", "32", "128", str(1 << 17), str(1 << 19), str(1 << 25)):
+    # bit26: level 0 straight from registers in the tcgen05.ld.16x256b fragment layout (no staging, no TMA store)
+    for flags in ("65536", "32", "128", str(1 << 17), str(1 << 19), str(1 << 25), str(1 << 26)):
         res = _run_with_env(code, {"CF_TC_FLAGS": flags})
         assert res.returncode == 0 and "F16_OK" in res.stdout, flags + res.stdout + res.stderr
