@@ -1564,6 +1564,9 @@ int corr_volume_tensor_core(const float *f1, const float *f2, int B, int D, int 
     // level-1 scratch has no room then: level-1 rows leave as per-lane 16-byte stores.  Measured SLOWER at 64 x 60x80: 2476
     // against 1985 us for the twenty single boxes on the same box (one buffer per lane quarter: every tile waits for its
     // predecessor's box to leave, and two named barriers) -- only on request (flags bit19).  flags bit17 switches b_sw64 off.
+    // (Also measured: the epilogue's shared-memory accesses as explicit st.shared / ld.shared asm instead of the generic ST.E / LD.E
+    //  the compiler emits for the aligned-up buffer pointer: 2545-2568 against 2221-2243 us on one box -- volatile asm with a memory
+    //  clobber pins every store in program order between the TMEM loads and fences; the plain C++ dereferences stay.)
     // Most of that loss is the level-1 rows: per-lane 16-byte stores alone (flags bit24, single boxes) cost 2485 against 2015 us
     // at this shape.  A variant with one {32 x 32 x 3 | 2} box per WARP (no barrier, 8 stores per tile; write_probe: 5.8 against
     // 4.9 TB/s for the stores alone, 4.3 against 3.7 with the operand loads) measured 2630 us with the same level-1 stores,
