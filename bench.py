@@ -158,7 +158,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, watts, reasons, capped = [], [], [], set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             parts = [p.strip() for p in line.split(",")]
@@ -169,12 +169,19 @@ class ClockSampler:
                 mx.append(float(parts[1]))
             except ValueError:
                 continue
+            try:
+                watts.append(float(parts[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+                    capped += n == "sw_power_cap"
         # median over the samples taken under load (the upper half: idle samples sit at the idle clock)
         load = sorted(sm)[len(sm) // 2:] if sm else []
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_min_mhz_under_load": min(load) if load else None, "power_w_max": max(watts) if watts else None,
+                "sw_power_cap_share_of_samples": capped / len(sm) if sm else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
